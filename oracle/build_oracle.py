@@ -1,0 +1,24 @@
+"""Builds the C restatement (oracle/mmi_oracle.c) into oracle/_build/libmmi_oracle.so.
+
+TEST INFRASTRUCTURE ONLY.  Building the checker is not using it: __graft_entry__.build()
+calls this so the .so travels to the GPU box with the snapshot.
+"""
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(force: bool = False) -> str:
+    out_dir = os.path.join(_HERE, '_build')
+    os.makedirs(out_dir, exist_ok=True)
+    src = os.path.join(_HERE, 'mmi_oracle.c')
+    out = os.path.join(out_dir, 'libmmi_oracle.so')
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-fno-fast-math', '-shared', '-fPIC', '-o', out,
+                               src, '-lm'])
+    return out
+
+
+if __name__ == '__main__':
+    print(build(force=True))

@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Writes tests/golden/* by running the REFERENCE's own code (build container only).
+
+    python tools/make_golden.py            # needs /root/reference
+
+Everything written here is a small fixture that travels to the GPU box, where
+/root/reference does not exist.  Fixtures:
+
+  img00_body.npz        real SHAPY_A output shipped by the reference
+                        (samples/shapy_fit_for_virtual_measurements/img_00.npz): v_shaped,
+                        faces (int32), raw/decoded poses, camera, joints, proj_joints,
+                        golden measurements; plus 3 more real v_shaped bodies from
+                        regressor/hbw_evaluation/example_shapy_prediction.npz.
+  measurement_landmarks.json   the 5 (face_idx, bc) landmarks BodyMeasurements reads from
+                        mesh-mesh-intersection/data/{measurement_defitions,smplx_measurements}.yaml
+  ref_smplx.npz         reference lbs()/SMPLX.forward outputs on the seeded synthetic model
+  ref_head.npz          reference IterativeRegression + ContinuousRotReprDecoder outputs
+  ref_hrnet.npz         reference HighResolutionNet outputs on the seeded synthetic checkpoint
+  hrnet_keys.json       the 1 967 state-dict keys/shapes of the reference backbone (sha256 + list)
+  ref_measure.json      oracle/measure (quirk-faithful op.cu emulation) results on the 4 real bodies
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+G = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(G, exist_ok=True)
+REF = ref_shim.REF
+
+
+def body_fixture():
+    d = ref_shim.load_img00()
+    ex = np.load(os.path.join(REF, 'regressor/hbw_evaluation/example_shapy_prediction.npz'))
+    np.savez_compressed(
+        os.path.join(G, 'img00_body.npz'),
+        v_shaped=d['v_shaped'].astype(np.float32), faces=d['faces'].astype(np.int32),
+        vertices=d['vertices'].astype(np.float32),
+        raw_global_rot=d['raw_global_rot'], global_rot=d['global_rot'],
+        raw_body_pose=d['raw_body_pose'], body_pose=d['body_pose'], betas=d['betas'],
+        camera=d['camera'], joints=d['joints'], proj_joints=d['proj_joints'],
+        meas_names=np.array(['mass', 'height', 'chest', 'waist', 'hips']),
+        meas_values=np.array([d['measurements'][k] for k in ['mass', 'height', 'chest', 'waist', 'hips']],
+                             dtype=np.float64),
+        extra_v_shaped=ex['v_shaped'].astype(np.float32))
+    import yaml
+    mv = yaml.safe_load(open(os.path.join(REF, 'mesh-mesh-intersection/data/smplx_measurements.yaml')))
+    md = yaml.safe_load(open(os.path.join(REF, 'mesh-mesh-intersection/data/measurement_defitions.yaml')))
+    lm = {}
+    for out_name, src in [('head_top', 'HeadTop'), ('left_heel', 'HeelLeft'), ('chest', md['CW_p'][0]),
+                          ('waist', md['BW_p'][0]), ('hips', md['IW_p'][0])]:
+        lm[out_name] = dict(name=src, face_idx=int(mv[src]['face_idx']), bc=[float(x) for x in mv[src]['bc']])
+    json.dump(lm, open(os.path.join(G, 'measurement_landmarks.json'), 'w'), indent=1)
+    print('img00_body.npz, measurement_landmarks.json', lm)
+
+
+def smplx_fixture():
+    from shapy_b200 import synth
+    ref = ref_shim.load()
+    model = synth.make_smplx()
+    g = torch.Generator().manual_seed(11)
+    B = 3
+    betas = torch.randn(B, 10, generator=g)
+    raw = torch.randn(B, 22 * 6, generator=g) * 0.4 + synth.mean_params()[:132]
+    dec1, dec21 = ref.pu.ContinuousRotReprDecoder(1), ref.pu.ContinuousRotReprDecoder(21)
+    with torch.no_grad():
+        grot = dec1(raw[:, :6].contiguous())
+        bpose = dec21(raw[:, 6:].contiguous())
+        out = ref_shim.smplx_forward_ref(model, betas, grot, bpose)
+        # config 1: T-pose, B=1
+        eye = torch.eye(3).view(1, 1, 3, 3)
+        out_t = ref_shim.smplx_forward_ref(model, betas[:1], eye.clone(), eye.expand(1, 21, -1, -1).contiguous())
+        # large head rotation to exercise the dynamic-contour LUT on both sides
+        raw2 = raw.clone()
+        aa = torch.tensor([[0.0, 0.9, 0.0], [0.0, -1.2, 0.1], [0.2, 0.3, 0.0]])
+        R = ref.rot.batch_rodrigues(aa)
+        # neck joint 12 sits at body_pose index 11 -> flat offset 6 + 11 * 6
+        raw2[:, 6 + 11 * 6: 6 + 12 * 6] = R[:, :, :2].reshape(B, 6)
+        grot2, bpose2 = dec1(raw2[:, :6].contiguous()), dec21(raw2[:, 6:].contiguous())
+        out2 = ref_shim.smplx_forward_ref(model, betas, grot2, bpose2)
+    np.savez_compressed(
+        os.path.join(G, 'ref_smplx.npz'), betas=betas.numpy(), raw=raw.numpy(), global_rot=grot.numpy(),
+        body_pose=bpose.numpy(), vertices=out['vertices'].numpy(), joints=out['joints'].numpy(),
+        v_shaped=out['v_shaped'].numpy(), t_vertices=out_t['vertices'].numpy(), t_joints=out_t['joints'].numpy(),
+        raw2=raw2.numpy(), joints2=out2['joints'].numpy(), vertices2_sub=out2['vertices'][:, ::97].numpy())
+    print('ref_smplx.npz', out['vertices'].shape, out['joints'].shape)
+
+
+def head_fixture():
+    from shapy_b200 import synth
+    ref = ref_shim.load()
+    mlp = ref.net.MLP(2048 + 145, 145, layers=[1024, 1024], activation={'type': 'none'},
+                      normalization={'type': 'none'}, dropout=0.5, gain=0.01)
+    it = ref.net.IterativeRegression(mlp, synth.mean_params().view(1, -1), num_stages=3).eval()
+    sd = synth.make_head_state_dict()
+    it.load_state_dict({k[len('regressor.'):]: v for k, v in sd.items()})
+    g = torch.Generator().manual_seed(12)
+    feats = torch.randn(5, 2048, generator=g).abs() * 0.5
+    with torch.no_grad():
+        params, _ = it(feats)
+    np.savez_compressed(os.path.join(G, 'ref_head.npz'), feats=feats.numpy(),
+                        params=np.stack([p.numpy() for p in params]))
+    print('ref_head.npz', params[-1].shape)
+
+
+def hrnet_fixture():
+    from shapy_b200 import synth
+    m = ref_shim.build_hrnet()
+    sd0 = m.state_dict()
+    keys = [[k, list(v.shape)] for k, v in sd0.items()]
+    digest = hashlib.sha256('\n'.join(f'{k} {s}' for k, s in keys).encode()).hexdigest()
+    json.dump(dict(sha256=digest, n=len(keys), keys=keys), open(os.path.join(G, 'hrnet_keys.json'), 'w'))
+    m.load_state_dict(synth.make_state_dict(sd0, seed=1))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        out = m(x)
+        x64 = torch.randn(1, 3, 64, 96, generator=g)
+        out64 = m(x64)
+    np.savez_compressed(
+        os.path.join(G, 'ref_hrnet.npz'), concat=out['concat'].numpy(),
+        layer1_sub=out['layer1'][:, ::7, ::5, ::5].numpy(), layer4=out['layer4'][:, ::16].numpy(),
+        concat64=out64['concat'].numpy())
+    print('ref_hrnet.npz', out['concat'].shape, float(out['concat'].abs().mean()), len(keys), digest[:12])
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet']
+    torch.set_num_threads(8)
+    if 'body' in which:
+        body_fixture()
+    if 'smplx' in which:
+        smplx_fixture()
+    if 'head' in which:
+        head_fixture()
+    if 'hrnet' in which:
+        hrnet_fixture()
