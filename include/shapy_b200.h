@@ -1,0 +1,199 @@
+/* shapy_b200 -- C ABI of the B200-native SHAPY inference hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / a CUDA stream
+ * (passed as void* so the header needs no CUDA include) and returns 0 on success or
+ * a negative shapy_b200 error / positive cudaError_t code; shapy_last_error() gives
+ * the message.  No torch types.  All device work is stream-ordered on `stream`; no
+ * call synchronises the device.  Outputs are caller-owned device buffers.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference
+ * repo):
+ *
+ *   shapy_smplx_*        lbs()                      regressor/human_shape/models/body_models/lbs.py:99-196
+ *                        SMPLX.forward              regressor/human_shape/models/body_models/body_models.py:628-767
+ *                        SMPL.forward_shape         body_models.py:292-302
+ *                        ContinuousRotReprDecoder   regressor/human_shape/models/common/pose_utils.py:138-153
+ *                        WeakPerspectiveCamera      regressor/human_shape/models/camera/camera_projection.py:181-213
+ *   shapy_measure_*      BodyMeasurements.forward   mesh-mesh-intersection/body_measurements/body_measurements.py:217-246
+ *   shapy_mmi_forward    mesh_to_mesh_forward       mesh-mesh-intersection/src/mesh_mesh_intersect.cpp:36-64
+ *                                                   + src/mesh_mesh_intersect_cuda_op.cu:969-1079
+ *   shapy_head_*         IterativeRegression.forward regressor/human_shape/models/common/networks.py:536-592
+ *   shapy_hrnet_*        HighResolutionNet.forward  regressor/human_shape/models/backbone/hrnet.py:426-498
+ */
+#ifndef SHAPY_B200_H_
+#define SHAPY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHAPY_OK 0
+#define SHAPY_ERR_ARG (-1)      /* bad argument (null pointer, unsupported size) */
+#define SHAPY_ERR_STATE (-2)    /* object not bound / wrong device */
+#define SHAPY_ERR_UNSUPPORTED (-3)
+#define SHAPY_ERR_OVERFLOW (-4) /* a fixed-capacity device buffer overflowed */
+
+const char *shapy_last_error(void);
+int shapy_version(void);
+/* number of kernels this library launched since process start (all entry points) */
+long long shapy_launch_count(void);
+
+/* ------------------------------------------------------------------ SMPL-X */
+typedef struct shapy_smplx shapy_smplx_t;
+
+/* Dense model tensors exactly as the reference registers them as buffers
+ * (body_models.py:112-166, 563-597).  HOST pointers, fp32 / int64, row-major. */
+typedef struct {
+  int num_verts;               /* V  (10475) */
+  int num_joints;              /* J  (55)    */
+  int num_betas;               /* NB (10)  shapedirs is (V,3,NB) */
+  int num_expr;                /* NE (10)  expr_dirs is (V,3,NE); may be 0 */
+  int num_faces;               /* F  (20908) */
+  const float *v_template;     /* (V,3) */
+  const float *shapedirs;      /* (V,3,NB) */
+  const float *expr_dirs;      /* (V,3,NE) or NULL */
+  const float *posedirs;       /* ((J-1)*9, V*3) */
+  const float *J_regressor;    /* (J,V) */
+  const float *lbs_weights;    /* (V,J) */
+  const int64_t *parents;      /* (J), parents[0] = -1 */
+  const int64_t *faces;        /* (F,3) */
+  int num_static_lmk;          /* 51 */
+  const int64_t *lmk_faces_idx;        /* (L) */
+  const float *lmk_bary_coords;        /* (L,3) */
+  int num_dyn_lmk;             /* 17, 0 disables use_face_contour */
+  int num_dyn_rows;            /* 79 */
+  const int64_t *dynamic_lmk_faces_idx;   /* (rows, D) */
+  const float *dynamic_lmk_bary_coords;   /* (rows, D, 3) */
+  int neck_chain_len;          /* 6 */
+  const int64_t *neck_kin_chain;       /* e.g. [15,12,9,6,3,0] */
+  int num_extra;               /* 14 rows of the J14 regressor, 0 disables */
+  const float *extra_joint_regressor;  /* (num_extra, V) */
+  int num_overwrite;           /* len(source_idxs) */
+  const int64_t *source_idxs;  /* joints[:, source] = reg[:, target] */
+  const int64_t *target_idxs;
+} shapy_smplx_desc_t;
+
+int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t *desc);
+void shapy_smplx_destroy(shapy_smplx_t *m);
+int shapy_smplx_num_keypoints(const shapy_smplx_t *m);          /* J + L + D (123) */
+const int32_t *shapy_smplx_faces_i32(const shapy_smplx_t *m);   /* device (F,3) int32 */
+size_t shapy_smplx_workspace_bytes(const shapy_smplx_t *m, int batch);
+
+/* 6D -> rotation matrices: raw (n, 6) row-major 3x2 -> rot (n, 3, 3). */
+int shapy_decode_rot6d(const float *raw, int n, float *rot, void *stream);
+
+/* Full SMPL-X evaluation for `batch` bodies.
+ *   betas   (B, NB)                 device fp32
+ *   rot     (B, n_rot, 3, 3)        rotations of the first n_rot joints of the full pose
+ *                                   [global, body(21), jaw, leye, reye, lhand(15), rhand(15)];
+ *                                   the remaining joints are identity (SHAPY_A: n_rot = 22)
+ *   expr    (B, NE) or NULL (zeros)
+ *   camera  (B, 3) or NULL; when given, proj_joints = softplus(c0) * (joints_xy + c[1:3])
+ * outputs (any may be NULL): vertices (B,V,3), v_shaped (B,V,3), joints (B,K,3), proj_joints (B,K,2)
+ */
+int shapy_smplx_forward(const shapy_smplx_t *m, const float *betas, const float *rot, int n_rot,
+                        const float *expr, const float *camera, int batch, float *vertices, float *v_shaped,
+                        float *joints, float *proj_joints, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* v_shaped = v_template + shapedirs . betas  (T-pose path, BASELINE configs 1 and 4) */
+int shapy_smplx_forward_shape(const shapy_smplx_t *m, const float *betas, int batch, float *v_shaped,
+                              void *stream);
+
+/* ------------------------------------------------------- virtual measurements */
+typedef struct {
+  int face_idx[5];      /* head_top, left_heel, chest, waist, hips landmark faces */
+  float bc[5][3];       /* barycentrics */
+} shapy_measure_landmarks_t;
+
+/* v_shaped (B,V,3), faces int32 (F,3) device.  out (B,5) = mass, height, chest, waist, hips.
+ * plane_points (optional, (B,3,max_points,3)) / plane_counts (optional, (B,3) int32) receive the
+ * reference-selected intersection points of each slicing plane.  status (device int32[1], may be
+ * NULL) is set non-zero if any plane exceeded max_points (SHAPY_ERR_OVERFLOW semantics). */
+int shapy_measure_forward(const float *v_shaped, const int32_t *faces, int batch, int num_verts, int num_faces,
+                          const shapy_measure_landmarks_t *lm, float *out, float *plane_points,
+                          int32_t *plane_counts, int max_points, int32_t *status, void *stream);
+
+/* Same on explicit triangles (B,F,3,3) -- the tensor BodyMeasurements.forward receives. */
+int shapy_measure_forward_tris(const float *triangles, int batch, int num_faces,
+                               const shapy_measure_landmarks_t *lm, float *out, float *plane_points,
+                               int32_t *plane_counts, int max_points, int32_t *status, void *stream);
+
+/* Drop-in for mesh_mesh_intersect_cuda.mesh_to_mesh_forward: query (B,Q,3,3), target (B,F,3,3) fp32;
+ * collision_faces (B,Q*M) int64 pre-filled by the callee with -1; collision_bcs (B,Q*M,2,3) with 0. */
+size_t shapy_mmi_workspace_bytes(int batch, int num_query, int num_target);
+int shapy_mmi_forward(const float *query, const float *target, int batch, int num_query, int num_target,
+                      int max_collisions, int64_t *collision_faces, float *collision_bcs, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------ regression head */
+/* params_out (num_stages, B, P).  W0 (H0, F+P), W1 (H1, H0), W2 (P, H1) row-major as nn.Linear stores
+ * them; mean (P).  workspace >= shapy_head_workspace_bytes. */
+size_t shapy_head_workspace_bytes(int batch, int feat_dim, int param_dim, int h0, int h1);
+int shapy_head_forward(const float *feats, int batch, int feat_dim, int param_dim, int h0, int h1,
+                       const float *W0, const float *b0, const float *W1, const float *b1, const float *W2,
+                       const float *b2, const float *mean, int num_stages, float *params_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* -------------------------------------------------------------------- HRNet */
+typedef struct shapy_hrnet shapy_hrnet_t;
+
+/* One convolution of the backbone, BN already folded by the caller's choice: the library folds
+ * scale into the weights itself when `bn_*` are given.  HOST pointers. */
+typedef struct {
+  int cin, cout, ksize, stride; /* ksize 1 or 3, stride 1 or 2, padding ksize/2 */
+  const float *weight;          /* (cout, cin, k, k) */
+  const float *bias;            /* (cout) or NULL */
+  const float *bn_weight, *bn_bias, *bn_mean, *bn_var; /* (cout) each or all NULL */
+  float bn_eps;
+} shapy_conv_desc_t;
+
+enum { SHAPY_OP_STEM = 0, SHAPY_OP_CONV = 1, SHAPY_OP_FUSE = 2, SHAPY_OP_POOL = 3 };
+
+/* Program of the network: a flat list of ops over numbered activation slots.  A slot is a
+ * (B, H/div, W/div, C) NHWC tensor; outputs may write a channel slice of a wider slot
+ * (out_coff / slot channels) which is how the 4x384 concat is formed without a copy. */
+typedef struct {
+  int kind;          /* SHAPY_OP_* */
+  int conv;          /* index into the conv table (STEM / CONV) */
+  int in_slot;       /* -1 = network input (STEM) */
+  int out_slot, out_coff;
+  int res_slot;      /* residual added before ReLU, -1 none */
+  int relu;
+  /* FUSE: out = relu(sum_i up(in_i)); in_i at scale 2^shift_i coarser than out (nearest) */
+  int n_in;
+  int fuse_in[4];
+  int fuse_shift[4];
+} shapy_op_t;
+
+typedef struct {
+  int channels;      /* total channels of the slot */
+  int div;           /* spatial divisor w.r.t. the network input (4, 8, 16, 32, 2) */
+} shapy_slot_t;
+
+/* mode: 0 = fp16 operands, single pass (BASELINE config 2);
+ *       1 = split-fp16 (hi + lo planes, 3 MMAs per tile, ~fp32 accuracy; parity mode);
+ * engine: 0 = tcgen05 implicit GEMM where the shape allows, 1 = SIMT fp32 everywhere (debug). */
+int shapy_hrnet_create(shapy_hrnet_t **out, const shapy_conv_desc_t *convs, int n_convs, const shapy_op_t *ops,
+                       int n_ops, const shapy_slot_t *slots, int n_slots, int feat_slot, int mode, int engine);
+void shapy_hrnet_destroy(shapy_hrnet_t *p);
+size_t shapy_hrnet_workspace_bytes(const shapy_hrnet_t *p, int batch, int height, int width);
+/* images (B,3,H,W) fp32 NCHW device; feats (B, C_feat) fp32 device. */
+int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int batch, int height, int width, float *feats,
+                        void *workspace, size_t workspace_bytes, void *stream);
+/* copies slot `slot` (after a forward) to dst as fp32 NCHW (B,C,H/div,W/div); for tests. */
+int shapy_hrnet_read_slot(shapy_hrnet_t *p, int slot, float *dst, void *stream);
+double shapy_hrnet_flops(const shapy_hrnet_t *p, int batch, int height, int width);
+
+/* Standalone conv for unit tests of the implicit-GEMM kernel: x (B,H,W,Cin) fp32 NHWC device,
+ * y (B,Ho,Wo,Cout) fp32 NHWC device, res optional (same shape as y). */
+int shapy_conv_test(const shapy_conv_desc_t *conv, const float *x, const float *res, int batch, int height,
+                    int width, int relu, int mode, int engine, float *y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHAPY_B200_H_ */

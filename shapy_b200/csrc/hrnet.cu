@@ -1,0 +1,282 @@
+// HRNet-W48 executor: a flat program of STEM / CONV / FUSE / POOL ops over numbered NHWC activation
+// slots (built by the Python host mirror from the reference module tree,
+// regressor/human_shape/models/backbone/hrnet.py:202-498), run as a fixed sequence of launches with no
+// host synchronisation, so it can be captured in a CUDA graph.
+//   create : folds BatchNorm into the conv weights (scale) and a per-channel bias (shift), packs the
+//            weights as [tap][cout][cin] fp16 hi/lo planes on the device.
+//   bind   : (first forward for a given workspace / batch / image size) lays the slots out in the
+//            caller's workspace and encodes the TMA descriptors of every tcgen05 convolution.
+//   forward: ~380 launches (331 convs + fuse sums + pool) instead of the reference's ~1100.
+#include <cmath>
+#include <cstring>
+
+#include "conv.cuh"
+
+using namespace shapy;
+
+struct shapy_hrnet {
+  std::vector<ConvW> convs;
+  std::vector<shapy_op_t> ops;
+  std::vector<shapy_slot_t> slots;
+  int feat_slot = -1, mode = 1, engine = 0;
+  std::vector<void *> allocs;
+  // binding
+  void *ws = nullptr;
+  int B = 0, H = 0, W = 0;
+  std::vector<ActView> views;
+  std::vector<UmmaPlan *> plans;  // per op (null when the op does not use the tcgen05 engine)
+};
+
+static void free_plans(shapy_hrnet *p) {
+  for (auto *u : p->plans) if (u) umma_plan_destroy(u);
+  p->plans.clear();
+}
+
+template <typename T>
+static T *dev_upload(std::vector<void *> &allocs, const std::vector<T> &h, cudaError_t &err) {
+  T *d = nullptr;
+  if (err != cudaSuccess) return nullptr;
+  err = cudaMalloc((void **)&d, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (err != cudaSuccess) return nullptr;
+  allocs.push_back(d);
+  if (!h.empty()) err = cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+
+// Folds BN and packs one conv.  Returns false on CUDA failure.
+static bool pack_conv(const shapy_conv_desc_t &c, bool stem, ConvW &out, std::vector<void *> &allocs, cudaError_t &err) {
+  const int taps = c.ksize * c.ksize;
+  std::vector<float> scale(c.cout, 1.f), bias(c.cout, 0.f);
+  for (int o = 0; o < c.cout; ++o) {
+    float b = c.bias ? c.bias[o] : 0.f;
+    if (c.bn_weight) {
+      // y = (conv + b - mean) * gamma / sqrt(var + eps) + beta   (eval-mode BatchNorm2d)
+      float s = c.bn_weight[o] / std::sqrt(c.bn_var[o] + c.bn_eps);
+      scale[o] = s;
+      bias[o] = (b - c.bn_mean[o]) * s + c.bn_bias[o];
+    } else {
+      bias[o] = b;
+    }
+  }
+  out.cin = c.cin; out.cout = c.cout; out.ksize = c.ksize; out.stride = c.stride;
+  out.bias = dev_upload(allocs, bias, err);
+  if (stem) {
+    std::vector<float> wf((size_t)taps * c.cin * c.cout);
+    for (int o = 0; o < c.cout; ++o)
+      for (int i = 0; i < c.cin; ++i)
+        for (int t = 0; t < taps; ++t)
+          wf[((size_t)t * c.cin + i) * c.cout + o] = c.weight[((size_t)o * c.cin + i) * taps + t] * scale[o];
+    out.w_f32 = dev_upload(allocs, wf, err);
+    return err == cudaSuccess;
+  }
+  std::vector<__half> hi((size_t)taps * c.cout * c.cin), lo(hi.size());
+  for (int o = 0; o < c.cout; ++o)
+    for (int i = 0; i < c.cin; ++i)
+      for (int t = 0; t < taps; ++t) {
+        float v = c.weight[((size_t)o * c.cin + i) * taps + t] * scale[o];
+        __half h = __float2half_rn(v);
+        size_t d = ((size_t)t * c.cout + o) * c.cin + i;
+        hi[d] = h;
+        lo[d] = __float2half_rn((v - __half2float(h)) * kLoScale);
+      }
+  out.w_hi = dev_upload(allocs, hi, err);
+  out.w_lo = dev_upload(allocs, lo, err);
+  return err == cudaSuccess;
+}
+
+extern "C" int shapy_hrnet_create(shapy_hrnet_t **out, const shapy_conv_desc_t *convs, int n_convs,
+                                  const shapy_op_t *ops, int n_ops, const shapy_slot_t *slots, int n_slots,
+                                  int feat_slot, int mode, int engine) {
+  SHAPY_REQUIRE(out && convs && ops && slots && n_convs > 0 && n_ops > 0 && n_slots > 0, "shapy_hrnet_create: bad argument");
+  SHAPY_REQUIRE(mode == 0 || mode == 1, "shapy_hrnet_create: mode %d", mode);
+  auto *p = new shapy_hrnet();
+  p->ops.assign(ops, ops + n_ops);
+  p->slots.assign(slots, slots + n_slots);
+  p->feat_slot = feat_slot; p->mode = mode; p->engine = engine;
+  std::vector<char> is_stem(n_convs, 0);
+  for (auto &o : p->ops) {
+    if ((o.kind == SHAPY_OP_STEM || o.kind == SHAPY_OP_CONV) && (o.conv < 0 || o.conv >= n_convs)) {
+      delete p; set_error("op references conv %d of %d", o.conv, n_convs); return SHAPY_ERR_ARG;
+    }
+    if (o.kind == SHAPY_OP_STEM) is_stem[o.conv] = 1;
+  }
+  cudaError_t err = cudaSuccess;
+  p->convs.resize(n_convs);
+  for (int i = 0; i < n_convs; ++i) {
+    if (!pack_conv(convs[i], is_stem[i], p->convs[i], p->allocs, err)) break;
+  }
+  if (err != cudaSuccess) {
+    set_error("shapy_hrnet_create: %s", cudaGetErrorString(err));
+    shapy_hrnet_destroy(p);
+    return (int)err;
+  }
+  *out = p;
+  return SHAPY_OK;
+}
+
+extern "C" void shapy_hrnet_destroy(shapy_hrnet_t *p) {
+  if (!p) return;
+  free_plans(p);
+  for (void *a : p->allocs) cudaFree(a);
+  delete p;
+}
+
+static size_t slot_bytes(const shapy_hrnet *p, int s, int B, int H, int W) {
+  const shapy_slot_t &sl = p->slots[s];
+  size_t plane = (size_t)B * (H / sl.div) * (W / sl.div) * sl.channels * sizeof(__half);
+  return align_up(plane, 1024) * (p->mode ? 2 : 1);
+}
+
+extern "C" size_t shapy_hrnet_workspace_bytes(const shapy_hrnet_t *p, int B, int H, int W) {
+  if (!p || B <= 0 || H % 32 || W % 32) return 0;
+  size_t total = 1024;
+  for (size_t s = 0; s < p->slots.size(); ++s) total += slot_bytes(p, (int)s, B, H, W);
+  return total;
+}
+
+static ActView view_of(const shapy_hrnet *p, int slot, int coff, int C) {
+  ActView v = p->views[slot];
+  v.coff = coff;
+  v.C = C;
+  return v;
+}
+
+static int bind(shapy_hrnet *p, void *ws, int B, int H, int W) {
+  free_plans(p);
+  p->views.assign(p->slots.size(), ActView());
+  char *base = (char *)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  for (size_t s = 0; s < p->slots.size(); ++s) {
+    const shapy_slot_t &sl = p->slots[s];
+    ActView &v = p->views[s];
+    v.N = B; v.H = H / sl.div; v.W = W / sl.div; v.C = sl.channels; v.Ctot = sl.channels; v.coff = 0;
+    size_t plane = align_up((size_t)B * v.H * v.W * sl.channels * sizeof(__half), 1024);
+    v.hi = (__half *)base;
+    v.lo = p->mode ? (__half *)(base + plane) : nullptr;
+    base += plane * (p->mode ? 2 : 1);
+  }
+  p->plans.assign(p->ops.size(), nullptr);
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const shapy_op_t &o = p->ops[i];
+    if (o.kind != SHAPY_OP_CONV || p->engine == 1) continue;
+    const ConvW &w = p->convs[o.conv];
+    ActView in = view_of(p, o.in_slot, 0, w.cin), out = view_of(p, o.out_slot, o.out_coff, w.cout);
+    ActView res;
+    if (o.res_slot >= 0) res = view_of(p, o.res_slot, 0, w.cout);
+    if (!umma_supported(w, in, out)) continue;  // falls back to the SIMT engine for this layer
+    p->plans[i] = umma_plan_create(w, in, out, o.res_slot >= 0 ? &res : nullptr, o.relu != 0);
+    if (!p->plans[i]) return SHAPY_ERR_STATE;
+  }
+  p->ws = ws; p->B = B; p->H = H; p->W = W;
+  return SHAPY_OK;
+}
+
+extern "C" int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int B, int H, int W, float *feats,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+  SHAPY_REQUIRE(p && images && feats && workspace, "shapy_hrnet_forward: null argument");
+  SHAPY_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "shapy_hrnet_forward: image size %dx%d must be a multiple of 32", H, W);
+  SHAPY_REQUIRE(workspace_bytes >= shapy_hrnet_workspace_bytes(p, B, H, W), "shapy_hrnet_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->ws != workspace || p->B != B || p->H != H || p->W != W) {
+    int rc = bind(p, workspace, B, H, W);
+    if (rc) return rc;
+  }
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const shapy_op_t &o = p->ops[i];
+    int rc = SHAPY_OK;
+    switch (o.kind) {
+      case SHAPY_OP_STEM: {
+        const ConvW &w = p->convs[o.conv];
+        rc = launch_stem(w, images, B, H, W, view_of(p, o.out_slot, o.out_coff, w.cout), st);
+        break;
+      }
+      case SHAPY_OP_CONV: {
+        const ConvW &w = p->convs[o.conv];
+        if (p->plans[i]) {
+          rc = umma_plan_launch(p->plans[i], st);
+        } else {
+          ActView in = view_of(p, o.in_slot, 0, w.cin), out = view_of(p, o.out_slot, o.out_coff, w.cout), res;
+          if (o.res_slot >= 0) res = view_of(p, o.res_slot, 0, w.cout);
+          rc = launch_conv_simt(w, in, out, o.res_slot >= 0 ? &res : nullptr, o.relu != 0, st);
+        }
+        break;
+      }
+      case SHAPY_OP_FUSE: {
+        ActView ins[4];
+        const int C = p->slots[o.fuse_in[0]].channels;  // may be a channel slice of a wider output slot
+        for (int k = 0; k < o.n_in; ++k) ins[k] = view_of(p, o.fuse_in[k], 0, C);
+        rc = launch_fuse(ins, o.fuse_shift, o.n_in, view_of(p, o.out_slot, o.out_coff, C), o.relu != 0, st);
+        break;
+      }
+      case SHAPY_OP_POOL:
+        rc = launch_pool(p->views[o.in_slot], feats, st);
+        break;
+      default:
+        set_error("unknown op kind %d", o.kind);
+        rc = SHAPY_ERR_ARG;
+    }
+    if (rc) return rc;
+  }
+  return SHAPY_OK;
+}
+
+extern "C" int shapy_hrnet_read_slot(shapy_hrnet_t *p, int slot, float *dst, void *stream) {
+  SHAPY_REQUIRE(p && dst && slot >= 0 && slot < (int)p->slots.size() && p->ws, "shapy_hrnet_read_slot: bad argument / not bound");
+  return launch_nhwc_merge(p->views[slot], dst, true, (cudaStream_t)stream);
+}
+
+extern "C" double shapy_hrnet_flops(const shapy_hrnet_t *p, int B, int H, int W) {
+  if (!p) return 0.0;
+  double f = 0.0;
+  for (auto &o : p->ops) {
+    if (o.kind != SHAPY_OP_STEM && o.kind != SHAPY_OP_CONV) continue;
+    const ConvW &w = p->convs[o.conv];
+    const shapy_slot_t &so = p->slots[o.out_slot];
+    f += 2.0 * B * (H / so.div) * (W / so.div) * w.cout * (double)w.cin * w.ksize * w.ksize;
+  }
+  return f;
+}
+
+// Standalone convolution on fp32 NHWC buffers (unit tests of both engines).
+extern "C" int shapy_conv_test(const shapy_conv_desc_t *conv, const float *x, const float *res, int B, int H, int W,
+                               int relu, int mode, int engine, float *y, void *stream) {
+  SHAPY_REQUIRE(conv && x && y, "shapy_conv_test: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<void *> allocs;
+  cudaError_t err = cudaSuccess;
+  ConvW w;
+  int rc = SHAPY_OK;
+  UmmaPlan *plan = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    if (plan) umma_plan_destroy(plan);
+    for (void *a : allocs) cudaFree(a);
+  };
+  if (!pack_conv(*conv, false, w, allocs, err)) { cleanup(); set_error("conv_test: %s", cudaGetErrorString(err)); return (int)err; }
+  const int Ho = conv->stride == 2 ? H / 2 : H, Wo = conv->stride == 2 ? W / 2 : W;
+  auto make = [&](int n, int h, int ww, int c) {
+    ActView v;
+    v.N = n; v.H = h; v.W = ww; v.C = c; v.Ctot = c; v.coff = 0;
+    size_t bytes = (size_t)n * h * ww * c * sizeof(__half);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&v.hi, bytes);
+    if (err == cudaSuccess) allocs.push_back(v.hi);
+    if (mode && err == cudaSuccess) { err = cudaMalloc((void **)&v.lo, bytes); if (err == cudaSuccess) allocs.push_back(v.lo); }
+    return v;
+  };
+  ActView in = make(B, H, W, conv->cin), out = make(B, Ho, Wo, conv->cout), rv;
+  if (res) rv = make(B, Ho, Wo, conv->cout);
+  if (err != cudaSuccess) { cleanup(); set_error("conv_test: %s", cudaGetErrorString(err)); return (int)err; }
+  if ((rc = launch_nhwc_split(x, in, st))) { cleanup(); return rc; }
+  if (res && (rc = launch_nhwc_split(res, rv, st))) { cleanup(); return rc; }
+  if (engine == 0) {
+    plan = umma_plan_create(w, in, out, res ? &rv : nullptr, relu != 0);
+    if (!plan) { cleanup(); return SHAPY_ERR_UNSUPPORTED; }
+    rc = umma_plan_launch(plan, st);
+  } else {
+    rc = launch_conv_simt(w, in, out, res ? &rv : nullptr, relu != 0, st);
+  }
+  if (!rc) rc = launch_nhwc_merge(out, y, false, st);
+  cleanup();
+  cudaError_t e2 = cudaGetLastError();
+  if (!rc && e2 != cudaSuccess) { set_error("conv_test: %s", cudaGetErrorString(e2)); rc = (int)e2; }
+  return rc;
+}

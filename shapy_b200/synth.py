@@ -178,3 +178,44 @@ def mean_params() -> torch.Tensor:
     g[3] = -1
     cam = torch.tensor([math.log(math.exp(0.9) - 1), 0., 0.])
     return torch.cat([g, ident6.repeat(21), torch.zeros(10), cam])
+
+
+def load_landmarks(path=None) -> dict:
+    import json
+    return json.load(open(path or os.path.join(GOLDEN_DIR, 'measurement_landmarks.json')))
+
+
+def make_exp_cfg(smplx: dict = None, landmarks: dict = None) -> dict:
+    """Plain-dict equivalent of regressor/configs/b2a_expose_hrnet_demo.yaml:175-231 (SHAPY_A), with the
+    licensed assets replaced by the synthetic SMPL-X tensors and the measurement landmarks given inline."""
+    return {
+        'use_adv_training': False,
+        'network': {'type': 'SMPLXRegressor', 'smplx': {
+            'type': 'iterative-mlp', 'num_stages': 3, 'pose_last_stage': True, 'feature_key': 'concat',
+            'predict_hands': False, 'predict_face': False, 'compute_measurements': True,
+            'meas_landmarks': landmarks or load_landmarks(), 'use_b2a': False, 'use_a2b': False,
+            'backbone': {'type': 'hrnet', 'pretrained': False, 'hrnet': {'pretrained_path': ''}},
+            'mlp': {'layers': [1024, 1024], 'dropout': 0.5, 'gain': 0.01, 'normalization': {'type': 'none'},
+                    'activation': {'type': 'none'}},
+            'camera': {'pos_func': 'softplus', 'weak_persp': {'regress_translation': True, 'regress_scale': True}}}},
+        'body_model': {'type': 'smplx', 'model_folder': '', 'smplx': {
+            'data_struct': smplx or make_smplx(), 'betas': {'num': 10}, 'expression': {'num': 10},
+            'use_face_contour': True, 'global_rot': {'type': 'cont_rot_repr'}, 'body_pose': {'type': 'cont_rot_repr'}}},
+        'losses': {'body': {}},
+    }
+
+
+def build_synthetic_regressor(seed: int = 1, device=None):
+    """SMPLXRegressor (shapy_b200 mirror) with the seeded synthetic checkpoint loaded."""
+    from .human_shape.models import build_model
+    model = build_model(make_exp_cfg())['network']
+    sd = model.state_dict()
+    bb = {k[len('backbone.'):]: v for k, v in sd.items() if k.startswith('backbone.')}
+    new = {'backbone.' + k: v for k, v in make_state_dict(bb, seed=seed).items()}
+    new.update(make_head_state_dict(seed=seed))
+    missing, unexpected = model.load_state_dict(new, strict=False)
+    assert not unexpected, unexpected
+    model.eval()
+    if device is not None:
+        model = model.to(device)
+    return model
