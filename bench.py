@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native SHAPY hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+metric : bodies/sec, image -> SMPL-X vertices (+ betas, measurements), B = 64 per GPU (BASELINE configs[2],
+         "Full SHAPY_A regressor (HRNet + iterative head + fused SMPL-X), batch=64, 1xB200, fp32 tol 1e-4";
+         configs[4] shards 64 images per GPU, i.e. weak scaling).
+value  : whole-job bodies/s with the images already resident in HBM (CUDA events, max over ranks).
+e2e    : the same metric through the reference-facing module call with HOST buffers: pinned host images ->
+         H2D -> (NCCL scatter) -> SMPLXRegressor.forward -> (NCCL gather) -> D2H of vertices / betas /
+         measurements, all inside the timed region.
+roofline: the dominant kernel is the tcgen05 implicit-GEMM convolution (HRNet = ~99 % of the step);
+         achieved = algorithmic conv FLOPs (36.93 GFLOP / image @224^2) / HRNet device time.
+         `roofline_lbs` / `roofline_shape` report the HBM rooflines of the fused SMPL-X kernels.
+cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, "port") timed on the
+         box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'bodies/sec image->SMPL-X verts @ B=64 per GPU'
+CONV_GFLOP_PER_IMAGE_224 = 36.93            # SURVEY.md 8d (2 x 18.4665 GMAC), conv-only
+LBS_CONST_BYTES = 68.93e6                    # dense SMPL-X constants streamed by lbs()
+LBS_BODY_BYTES = 254896                      # per-body compulsory I/O
+SHAPE_CONST_BYTES = 1.38e6
+SHAPE_BODY_BYTES = 40 + 125700
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def cpu_reference_step(sd, smplx, lm, x):
+    """One pass of the CPU restatement of the reference path (oracle/) over the images `x`."""
+    import torch
+    from oracle import measure_oracle, net_oracle, smplx_oracle
+    with torch.no_grad():
+        feats = net_oracle.hrnet_forward({k[9:]: v for k, v in sd.items() if k.startswith('backbone.')}, x)['concat']
+        p = net_oracle.head_forward(sd, feats)[-1]
+        body = smplx_oracle.smplx_forward(smplx, p[:, 132:142], smplx_oracle.decode_6d(p[:, :6]),
+                                          smplx_oracle.decode_6d(p[:, 6:132]))
+    faces = smplx['faces_tensor'].numpy()
+    return [measure_oracle.measure(body['v_shaped'][b].numpy(), faces, lm) for b in range(x.shape[0])]
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path on the host cores (rank 0 only)."""
+    import torch
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    from shapy_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = synth.build_synthetic_regressor()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    smplx, lm = synth.make_smplx(), synth.load_landmarks()
+    sample = args.ref_sample
+    x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(sd, smplx, lm, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(sd, smplx, lm, x)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'bodies/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[2]: full SHAPY_A regressor, 224x224, CPU port of the reference path',
+                       'sample': f'{sample} bodies per step'},
+            'cpu_baseline': {'value': v, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{sample} images per step x {args.steps} steps (HRNet+head+SMPL-X+measurements)'},
+            'e2e': {'value': v, 'unit': 'bodies/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--batch', type=int, default=64, help='bodies per GPU')
+    ap.add_argument('--mode', type=int, default=1, help='1 = split-fp16 parity mode (1e-4), 0 = plain fp16 (config 2)')
+    ap.add_argument('--ref-sample', type=int, default=8)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from shapy_b200 import _lib, dist as sdist, synth
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = args.batch
+
+    model = synth.build_synthetic_regressor()
+    model.backbone.precision_mode = args.mode
+    sd_cpu = {k: v.clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    model = model.to(dev).eval()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return model(x_dev)
+
+    def timed(fn, k, pre=None):
+        """Sum of per-step device times (CUDA events on the launching stream), L2 flushed before each step."""
+        evs = []
+        barrier()
+        for _ in range(k):
+            flush.zero_()
+            if pre:
+                pre()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(W):
+        step_resident()
+    torch.cuda.synchronize()
+    n0 = L.shapy_launch_count()
+    step_resident()
+    torch.cuda.synchronize()
+    launches_per_step = L.shapy_launch_count() - n0
+
+    with ClockSampler(local_rank) as clk:
+        total_ms = timed(step_resident, K)
+    clocks = clk.summary()
+    ms_per_step = total_ms / K
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------------------------------------------------------- end-to-end with host buffers
+    per = B
+    out_host = {'vertices': torch.empty(world * per, 10475, 3).pin_memory(), 'betas': torch.empty(world * per, 10).pin_memory(),
+                'measurements': torch.empty(world * per, 5).pin_memory()} if rank == 0 else None
+    full_host = torch.randn(world * per, 3, 224, 224, generator=g).pin_memory() if rank == 0 else None
+
+    def step_e2e():
+        full_dev = full_host.to(dev, non_blocking=True) if rank == 0 else None
+        if world > 1:
+            res = sdist.sharded_forward(model, full_dev, per, device=dev)
+        else:
+            with torch.no_grad():
+                o = model(full_dev)
+            st = o['stage_02']
+            res = dict(vertices=st['vertices'], betas=st['betas'],
+                       measurements=torch.stack([o['measurements'][k] for k in ('mass', 'height', 'chest', 'waist', 'hips')], 1))
+        if rank == 0:
+            for k in out_host:
+                out_host[k].copy_(res[k], non_blocking=True)
+
+    for _ in range(W):
+        step_e2e()
+    e2e_ms = timed(step_e2e, K) / K
+    e2e_value = world * B / (e2e_ms * 1e-3)
+    h2d = world * per * 3 * 224 * 224 * 4
+    d2h = world * per * (10475 * 3 + 10 + 5) * 4
+
+    # ---------------------------------------------------------------- per-stage device times (rank 0, N = 1 view)
+    line = None
+    if True:
+        pk = peaks()
+        bb = model.backbone
+
+        def hr():
+            with torch.no_grad():
+                return bb(x_dev)['concat']
+        hr_ms = timed(hr, max(5, K // 2)) / max(5, K // 2)
+        conv_tf = B * CONV_GFLOP_PER_IMAGE_224 * 1e9 / (hr_ms * 1e-3) / 1e12
+        from shapy_b200 import ops
+        packed = model.model.packed(dev)
+        betas = torch.randn(B, 10, device=dev)
+        rot = ops.decode_rot6d((torch.randn(B, 132, device=dev) * 0.3 + synth.mean_params()[:132].to(dev)))
+
+        def lbs():
+            return ops.smplx_forward(packed, betas, rot)
+        for _ in range(3):
+            lbs()
+        lbs_ms = timed(lbs, 20) / 20
+        lbs_gbs = (LBS_CONST_BYTES + B * LBS_BODY_BYTES) / (lbs_ms * 1e-3) / 1e9
+        b4096 = torch.randn(4096, 10, device=dev).clamp(-3, 3)
+
+        def shp():
+            return ops.smplx_forward_shape(packed, b4096)
+        for _ in range(3):
+            shp()
+        shp_ms = timed(shp, 20) / 20
+        shp_gbs = (SHAPE_CONST_BYTES + 4096 * SHAPE_BODY_BYTES) / (shp_ms * 1e-3) / 1e9
+        vs4096 = shp()
+        faces = model.model.faces_i32
+        lmk = model.body_measurements.landmarks()
+
+        def meas():
+            return ops.measure(lmk, v_shaped=vs4096, faces_i32=faces)
+        for _ in range(2):
+            meas()
+        meas_ms = timed(meas, 5) / 5
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            smplx, lm = synth.make_smplx(), synth.load_landmarks()
+            n = args.ref_sample
+            xs = x_host[:n].clone()
+            t0 = time.perf_counter()
+            cpu_reference_step(sd_cpu, smplx, lm, xs)
+            dt = time.perf_counter() - t0
+            cpu = {'value': n / dt, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'{n} of the {B} images of one step, one pass (HRNet+head+SMPL-X+measurements), {dt:.1f} s'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'bodies/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (split-fp16 hi/lo tensor-core operands, fp32 accumulate)' if args.mode else 'f16',
+            'data': 'synthetic',
+            'config': {'workload': 'configs[2]: full SHAPY_A regressor (HRNet-W48 + iterative head + fused SMPL-X + '
+                                   'measurements), 224x224, batch 64 per GPU', 'batch_per_gpu': B,
+                       'l2': 'flushed (256 MB write) before every timed step', 'parallelism': f'dp{world}',
+                       'precision_mode': args.mode},
+            'e2e': {'value': e2e_value, 'unit': 'bodies/s', 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches_per_step * K),
+            'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'achieved': conv_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                         'frac': conv_tf / pk['tf_sustained'], 'traffic': None,
+                         'kernel': 'conv_umma_kernel (HRNet forward: all 331 convs + fuse + pool)',
+                         'ms': hr_ms, 'mma_flops_factor': 3 if args.mode else 1, 'peak_source': pk['source']},
+            'roofline_lbs': {'bound': 'hbm', 'achieved': lbs_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
+                             'frac': lbs_gbs / pk['hbm'], 'ms': lbs_ms, 'kernel': 'smplx_pose+vertex+joints, B=%d posed' % B},
+            'roofline_shape': {'bound': 'hbm', 'achieved': shp_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
+                               'frac': shp_gbs / pk['hbm'], 'ms': shp_ms, 'kernel': 'smplx_shape_kernel, 4096 bodies (config 4)'},
+            'measure_4096': {'ms': meas_ms, 'bodies_per_s': 4096 / (meas_ms * 1e-3)},
+        }
+        if cpu:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
