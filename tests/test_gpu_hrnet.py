@@ -58,10 +58,15 @@ def test_hrnet_fp16_mode_close(backbone, golden_dir):
 
 
 def test_hrnet_batch_independence(backbone):
+    """Images are independent: a permutation of the batch permutes the outputs bit for bit (same launch
+    configuration), and a sub-batch matches to fp32 rounding (the tile configuration depends on the batch
+    size, which changes the summation order)."""
     bb = backbone.cuda().eval()
     bb.engine, bb.precision_mode = 0, 1
     bb.invalidate()
     x = torch.randn(9, 3, 224, 224, generator=torch.Generator().manual_seed(5)).cuda()
     full = bb(x)['concat']
+    perm = torch.tensor([4, 0, 8, 2, 6, 1, 7, 3, 5]).cuda()
+    assert torch.equal(bb(x[perm].contiguous())['concat'], full[perm])
     part = bb(x[3:5].contiguous())['concat']
-    assert torch.equal(full[3:5], part)
+    assert rel(part, full[3:5]) < 1e-5
