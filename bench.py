@@ -83,6 +83,18 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: CPU affinity, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_reference_step(sd, smplx, lm, x):
     """One pass of the CPU restatement of the reference path (oracle/) over the images `x`."""
     import torch
@@ -102,15 +114,19 @@ def run_reference(args):
     if int(os.environ.get('RANK', '0')) != 0:
         return
     from shapy_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     model = synth.build_synthetic_regressor()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     smplx, lm = synth.make_smplx(), synth.load_landmarks()
-    sample = args.ref_sample
+    # calibrate on one body (this is also the warm-up), then size the per-step sample so that the K timed
+    # steps take about two minutes in total
+    x1 = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    t0 = time.perf_counter()
+    cpu_reference_step(sd, smplx, lm, x1)
+    t1 = time.perf_counter() - t0
+    sample = int(max(1, min(args.batch, 120.0 / max(args.steps, 1) / max(t1, 1e-3))))
     x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(0))
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(sd, smplx, lm, x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_reference_step(sd, smplx, lm, x)
@@ -136,7 +152,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--batch', type=int, default=64, help='bodies per GPU')
     ap.add_argument('--mode', type=int, default=1, help='1 = split-fp16 parity mode (1e-4), 0 = plain fp16 (config 2)')
-    ap.add_argument('--ref-sample', type=int, default=8)
+    ap.add_argument('--ref-sample', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -281,7 +297,7 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             torch.set_num_threads(cores)
             smplx, lm = synth.make_smplx(), synth.load_landmarks()
             n = args.ref_sample

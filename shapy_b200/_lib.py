@@ -70,6 +70,8 @@ _SIGS = {
     'shapy_head_forward': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
                                    c_void_p]),
+    'shapy_head_forward_collapsed': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                             c_void_p, c_void_p, c_size_t, c_void_p]),
     'shapy_hrnet_create': (c_int, [C.POINTER(c_void_p), C.POINTER(ConvDesc), c_int, C.POINTER(Op), c_int,
                                    C.POINTER(Slot), c_int, c_int, c_int, c_int]),
     'shapy_hrnet_destroy': (None, [c_void_p]),

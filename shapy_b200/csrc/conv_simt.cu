@@ -131,7 +131,7 @@ int launch_conv_simt(const ConvW &w, const ActView &in, const ActView &out, cons
 __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img, int N, int H, int W,
                                                    const float *__restrict__ wf, const float *__restrict__ bias, int Cout,
                                                    __half *out_hi, __half *out_lo, int ctot, int coff) {
-  extern __shared__ float ws[];  // [27][Cout] + bias[Cout]
+  extern __shared__ __align__(16) float ws[];  // [27][Cout] + bias[Cout]
   for (int i = threadIdx.x; i < 27 * Cout + Cout; i += blockDim.x) ws[i] = i < 27 * Cout ? wf[i] : bias[i - 27 * Cout];
   __syncthreads();
   const int Ho = H / 2, Wo = W / 2;
@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         float x = __ldg(img + (((size_t)n * 3 + ci) * H + ih) * W + iw);
-        const float *wr = ws + ((ky * 3 + kx) * 3 + ci) * Cout + g * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += x * wr[j];
+        const float4 *wr = reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * 3 + ci) * Cout + g * 8);
+        const float4 w0 = wr[0], w1 = wr[1];
+        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
+        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
       }
     }
   }

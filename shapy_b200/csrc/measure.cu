@@ -59,13 +59,14 @@ __device__ __forceinline__ bool better_next(double cx, double cz, float ax, floa
   return (wx * wx + wz * wz) > (ux * ux + uz * uz);
 }
 
-__global__ void __launch_bounds__(256) measure_kernel(MeasureArgs a) {
+constexpr int kMeasThreads = 512;
+__global__ void __launch_bounds__(kMeasThreads) measure_kernel(MeasureArgs a) {
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ float pts[3][kMaxPts][3];
   __shared__ int cnt[3];
   __shared__ float hs[3];
   __shared__ float lmy[2];
-  __shared__ float red[8];
+  __shared__ float red[kMeasThreads / 32];
   if (t < 3) cnt[t] = 0;
   if (t < 5) {
     mmi::Tri tr = load_tri(a, b, a.lm.face_idx[t]);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) measure_kernel(MeasureArgs a) {
   __syncthreads();
   if (t == 0) {
     float v = 0.f;
-    for (int i = 0; i < 8; ++i) v += red[i];
+    for (int i = 0; i < kMeasThreads / 32; ++i) v += red[i];
     a.out[(size_t)b * 5 + 0] = fabsf(v) / 6.0f * 985.0f;
     a.out[(size_t)b * 5 + 1] = fabsf(lmy[0] - lmy[1]);
   }
@@ -189,7 +190,7 @@ static int launch_measure(MeasureArgs a, void *stream) {
   for (int i = 0; i < 5; ++i)
     SHAPY_REQUIRE(a.lm.face_idx[i] >= 0 && a.lm.face_idx[i] < a.F, "landmark face %d out of range", a.lm.face_idx[i]);
   if (a.status) SHAPY_CUDA_TRY(cudaMemsetAsync(a.status, 0, sizeof(int), (cudaStream_t)stream));
-  measure_kernel<<<a.B, 256, 0, (cudaStream_t)stream>>>(a);
+  measure_kernel<<<a.B, kMeasThreads, 0, (cudaStream_t)stream>>>(a);
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;
 }

@@ -236,6 +236,30 @@ def head_forward(feats, W0, b0, W1, b1, W2, b2, mean, num_stages=3):
     return out
 
 
+def collapse_head(W0, b0, W1, b1, W2, b2, feat_dim):
+    """Contracts the activation-free 3-layer MLP into (MfT, Mp, c) in fp64 (host, once per weight load)."""
+    d = lambda t: t.detach().double().cpu()  # noqa: E731
+    W0, b0, W1, b1, W2, b2 = map(d, (W0, b0, W1, b1, W2, b2))
+    W21 = W2 @ W1
+    Mf = W21 @ W0[:, :feat_dim]
+    Mp = W21 @ W0[:, feat_dim:]
+    c = W2 @ (W1 @ b0 + b1) + b2
+    return Mf.t().contiguous().float(), Mp.contiguous().float(), c.float()
+
+
+def head_forward_collapsed(feats, MfT, Mp, c, mean, num_stages=3):
+    feats = _cuda_f32(feats, 'features')
+    B, Fd = feats.shape
+    P = mean.numel()
+    out = torch.empty(num_stages, B, P, dtype=torch.float32, device=feats.device)
+    ts = [_cuda_f32(t, 'head matrix') for t in (MfT, Mp, c, mean)]
+    with torch.cuda.device(feats.device):
+        ws = _WS.get('headc', B * P * 4, feats.device)
+        check(lib().shapy_head_forward_collapsed(ptr(feats), B, Fd, P, *[ptr(t) for t in ts], num_stages, ptr(out),
+                                                 ptr(ws), ws.numel(), stream_ptr()), 'head_forward_collapsed')
+    return out
+
+
 # ------------------------------------------------------------------------------------------- HRNet
 class HrnetPlan:
     """Owns a shapy_hrnet_t built from a conv table + op program (see human_shape/models/backbone/hrnet.py)."""

@@ -44,3 +44,20 @@ def test_head_vs_oracle(B):
                            c[p + 'output_layer.bias'], c['regressor.mean_param'].reshape(-1), 3)
     for k in range(3):
         assert rel(out[k], ref[k]) < 1e-5
+
+
+def test_collapsed_head_matches_reference_golden(golden_dir):
+    """The affine-collapsed evaluation (default in the module) against the reference's own outputs."""
+    from shapy_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'ref_head.npz'))
+    sd = synth.make_head_state_dict()
+    p = 'regressor.module.'
+    MfT, Mp, c = ops.collapse_head(sd[p + 'layer_000.0.weight'], sd[p + 'layer_000.0.bias'], sd[p + 'layer_001.0.weight'],
+                                   sd[p + 'layer_001.0.bias'], sd[p + 'output_layer.weight'], sd[p + 'output_layer.bias'], 2048)
+    out = ops.head_forward_collapsed(torch.from_numpy(g['feats']).cuda(), MfT.cuda(), Mp.cuda(), c.cuda(),
+                                     sd['regressor.mean_param'].reshape(-1).cuda(), 3)
+    for k in range(3):
+        assert rel(out[k], g['params'][k]) < 1e-5
+        d = out[k].cpu() - synth.mean_params()
+        dr = torch.from_numpy(g['params'][k]) - synth.mean_params()
+        assert rel(d, dr) < 1e-4
