@@ -178,21 +178,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const int pad = p.ksize / 2;
       const int per_tap = p.kpt / p.G;
       const uint32_t tx = (p.a_bytes + p.b_bytes) * (SPLIT ? 2u : 1u) * p.G;
-      for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
-        int w0, h0, n0, c_out0;
-        tile_coords(id, w0, h0, n0, c_out0);
-        for (int it = 0; it < iters; ++it) {
-          const int tap = it / per_tap, cb0 = (it % per_tap) * p.G;
-          const int ky = tap / p.ksize, kx = tap % p.ksize;
-          int mi = 0, x, y;
-          if (p.stride == 1) {
-            x = w0 + kx - pad; y = h0 + ky - pad;
-          } else {  // input row 2*oh + ky - 1: ky=0 -> odd rows, index oh-1; ky=1 -> even rows, oh; ky=2 -> odd rows, oh
-            mi = (ky != 1) * 2 + (kx != 1);
-            x = w0 + (kx == 0 ? -1 : 0); y = h0 + (ky == 0 ? -1 : 0);
-          }
-          mbar_wait(empty_bar(s), ph ^ 1);
-          if (elect_one()) {
+      if (elect_one()) {
+        for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
+          int w0, h0, n0, c_out0;
+          tile_coords(id, w0, h0, n0, c_out0);
+#pragma unroll 1
+          for (int it = 0; it < iters; ++it) {
+            const int tap = it / per_tap, cb0 = (it % per_tap) * p.G;
+            const int ky = tap / p.ksize, kx = tap % p.ksize;
+            int mi = 0, x, y;
+            if (p.stride == 1) {
+              x = w0 + kx - pad; y = h0 + ky - pad;
+            } else {  // input row 2*oh + ky - 1: ky=0 -> odd rows, index oh-1; ky=1 -> even rows, oh; ky=2 -> odd rows, oh
+              mi = (ky != 1) * 2 + (kx != 1);
+              x = w0 + (kx == 0 ? -1 : 0); y = h0 + (ky == 0 ? -1 : 0);
+            }
+            mbar_wait(empty_bar(s), ph ^ 1);
             mbar_expect_tx(full_bar(s), tx);
             const uint32_t sbase = smem_base + stage_bytes * s;
             for (int g = 0; g < p.G; ++g) {
@@ -204,11 +205,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               tma_load_3d(bb, &p.b_hi, full_bar(s), c0, c_out0, tap);
               if (SPLIT) tma_load_3d(bb + B_BLK, &p.b_lo, full_bar(s), c0, c_out0, tap);  // directly after the hi rows
             }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -221,11 +222,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         mbar_wait(acc_empty0 + 8u * buf, aph ^ 1);   // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * 256u, d1 = d0 + p.NT;
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t sbase = smem_base + stage_bytes * s;
+        if (elect_one()) {
+          int s_l = s;
+          uint32_t ph_l = ph;
+#pragma unroll 1
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(full_bar(s_l), ph_l);
+            tc_fence_after();
+            const uint32_t sbase = smem_base + stage_bytes * s_l;
             for (int g = 0; g < p.G; ++g) {
               const uint32_t kb = sbase + kblk_bytes * g;
               const uint64_t da0 = make_desc<KCH>(kb), dal0 = make_desc<KCH>(kb + A_BLK);
@@ -243,12 +247,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 }
               }
             }
-            umma_commit(empty_bar(s));
-            if (it == iters - 1) umma_commit(acc_full0 + 8u * buf);
+            umma_commit(empty_bar(s_l));
+            if (++s_l == p.stages) { s_l = 0; ph_l ^= 1; }
           }
-          __syncwarp();
-          if (++s == p.stages) { s = 0; ph ^= 1; }
+          umma_commit(acc_full0 + 8u * buf);
         }
+        __syncwarp();
+        for (int it = 0; it < iters; ++it) { if (++s == p.stages) { s = 0; ph ^= 1; } }
       }
     }
   } else {
@@ -505,39 +510,58 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           mbar_wait(a_full0 + 8u * slice, aph);
           if (p.dbg && lane == 0) atomicAdd(p.dbg + blockIdx.x * 16 + 3, (unsigned long long)(clock64() - m2));
           const uint32_t sa = a_base + slice * p.a_slice_bytes;
-          for (int tap = 0; tap < 9; ++tap) {
-            if (!p.b_resident) mbar_wait(b_full(bs), bph);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t bb = b_base + b_stage_bytes * (p.b_resident ? (cg * 9 + tap) : bs);
-              const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 16u;
-              const uint64_t db0 = make_desc<KCH>(bb);
-              // no-swizzle A descriptor: start address in 16-byte units in the low 14 bits
-              const uint64_t da_base = lbo_sbo | (uint64_t)(((sa + shift) & 0x3FFFF) >> 4);
-              const uint32_t first = (cg | tap) ? 1u : 0u;
-              for (int m = 0; m < p.MT; ++m) {
-                const uint32_t d0 = dbase + m * acc_cols, d1 = d0 + p.NT;
-                const uint64_t dam = da_base + (uint64_t)(m * 128);   // 128 rows x 16 B = 128 descriptor units
+          // one (tap) step: MT x KCH/16 k-steps x (2 | 1) MMAs
+          auto issue_tap = [&](int tap, uint32_t bb) {
+            const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 16u;
+            const uint64_t db0 = make_desc<KCH>(bb);
+            // no-swizzle A descriptor: start address in 16-byte units in the low 14 bits
+            const uint64_t da_base = lbo_sbo | (uint64_t)(((sa + shift) & 0x3FFFF) >> 4);
+            const uint32_t first = (cg | tap) ? 1u : 0u;
+            for (int m = 0; m < p.MT; ++m) {
+              const uint32_t d0 = dbase + m * acc_cols, d1 = d0 + p.NT;
+              const uint64_t dam = da_base + (uint64_t)(m * 128);   // 128 rows x 16 B = 128 descriptor units
 #pragma unroll
-                for (int ks = 0; ks < KCH / 16; ++ks) {
-                  const uint64_t da = dam + (uint64_t)(2 * ks) * ps16;
-                  const uint64_t ko = (uint64_t)(ks * 2);
-                  if (SPLIT) {
-                    umma_f16(d0, da, db0 + ko, p.idesc2, first | (ks ? 1u : 0u));      // [D0 | D1] (+)= A_hi . [B_hi | B_lo]^T
-                    umma_f16(d1, da + (uint64_t)PLANES * ps16, db0 + ko, p.idesc, 1);  // D1 += A_lo . B_hi^T
-                  } else {
-                    umma_f16(d0, da, db0 + ko, p.idesc, first | (ks ? 1u : 0u));
-                  }
+              for (int ks = 0; ks < KCH / 16; ++ks) {
+                const uint64_t da = dam + (uint64_t)(2 * ks) * ps16;
+                const uint64_t ko = (uint64_t)(ks * 2);
+                if (SPLIT) {
+                  umma_f16(d0, da, db0 + ko, p.idesc2, first | (ks ? 1u : 0u));      // [D0 | D1] (+)= A_hi . [B_hi | B_lo]^T
+                  umma_f16(d1, da + (uint64_t)PLANES * ps16, db0 + ko, p.idesc, 1);  // D1 += A_lo . B_hi^T
+                } else {
+                  umma_f16(d0, da, db0 + ko, p.idesc, first | (ks ? 1u : 0u));
                 }
               }
-              if (!p.b_resident) umma_commit(b_empty(bs));
-              if (tap == 8) {
-                umma_commit(a_empty0 + 8u * slice);
-                if (cg == p.ncg - 1) umma_commit(acc_full0 + 8u * buf);
-              }
+            }
+          };
+          if (p.b_resident) {
+            // weights are resident: all 9 taps of this channel group are issued by one elected lane in one go
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) issue_tap(tap, b_base + b_stage_bytes * (cg * 9 + tap));
+              umma_commit(a_empty0 + 8u * slice);
+              if (cg == p.ncg - 1) umma_commit(acc_full0 + 8u * buf);
             }
             __syncwarp();
-            if (!p.b_resident) { if (++bs == p.bstages) { bs = 0; bph ^= 1; } }
+          } else {
+            // streamed weights: the elected lane also waits for each weight block, so the whole channel group
+            // is issued from one uniform region (a per-tap elect + __syncwarp costs ~150 cycles per tap)
+            if (elect_one()) {
+              int bs_l = bs;
+              uint32_t bph_l = bph;
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(b_full(bs_l), bph_l);
+                tc_fence_after();
+                issue_tap(tap, b_base + b_stage_bytes * bs_l);
+                umma_commit(b_empty(bs_l));
+                if (++bs_l == p.bstages) { bs_l = 0; bph_l ^= 1; }
+              }
+              umma_commit(a_empty0 + 8u * slice);
+              if (cg == p.ncg - 1) umma_commit(acc_full0 + 8u * buf);
+            }
+            __syncwarp();
+            for (int tap = 0; tap < 9; ++tap) { if (++bs == p.bstages) { bs = 0; bph ^= 1; } }
           }
           if (++slice == 2) { slice = 0; aph ^= 1; }
         }

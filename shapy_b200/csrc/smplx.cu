@@ -359,33 +359,47 @@ __global__ void __launch_bounds__(128) smplx_joints_kernel(JointsArgs a) {
 // shape coefficients of that coordinate live in registers and are reused for SB bodies, so the only
 // HBM traffic is the (B, 3V) output stream (S and T are 1.4 MB and stay in L2).
 constexpr int SB = 64;
+constexpr int SBP = 12;   // padded beta row (float4 x 3) so a body's coefficients are 3 broadcast LDS.128
 template <int NB>
 __global__ void __launch_bounds__(256) smplx_shape_kernel(const float *__restrict__ T, const float *__restrict__ S,
                                                           const float *__restrict__ betas, int V3, int B,
                                                           float *__restrict__ out) {
-  __shared__ float bs[SB][NB];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  static_assert(NB <= SBP, "beta row padding");
+  __shared__ __align__(16) float bs[SB][SBP];
+  // two coordinates per thread (c and c + 256): the same 3 LDS.128 of betas feed 20 FMAs
+  const int c0 = blockIdx.x * 512 + threadIdx.x, c1 = c0 + 256;
   const int b0 = blockIdx.y * SB;
-  for (int i = threadIdx.x; i < SB * NB; i += blockDim.x) {
-    int b = b0 + i / NB;
-    bs[i / NB][i % NB] = b < B ? betas[(size_t)b * NB + i % NB] : 0.f;
+  for (int i = threadIdx.x; i < SB * SBP; i += blockDim.x) {
+    int b = b0 + i / SBP, l = i % SBP;
+    bs[i / SBP][l] = (b < B && l < NB) ? betas[(size_t)b * NB + l] : 0.f;
   }
-  float s[NB], t0 = 0.f;
-  if (c < V3) {
-    t0 = T[c];
+  float s0[SBP], s1[SBP], t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int l = 0; l < NB; ++l) s[l] = S[(size_t)l * V3 + c];
+  for (int l = 0; l < SBP; ++l) { s0[l] = 0.f; s1[l] = 0.f; }
+  if (c0 < V3) {
+    t0 = T[c0];
+#pragma unroll
+    for (int l = 0; l < NB; ++l) s0[l] = S[(size_t)l * V3 + c0];
+  }
+  if (c1 < V3) {
+    t1 = T[c1];
+#pragma unroll
+    for (int l = 0; l < NB; ++l) s1[l] = S[(size_t)l * V3 + c1];
   }
   __syncthreads();
-  if (c >= V3) return;
   const int nb = min(SB, B - b0);
-  float *o = out + (size_t)b0 * V3 + c;
-#pragma unroll 4
+  float *o = out + (size_t)b0 * V3;
+#pragma unroll 2
   for (int i = 0; i < nb; ++i) {
-    float v = t0;
+    const float4 q0 = *reinterpret_cast<const float4 *>(&bs[i][0]);
+    const float4 q1 = *reinterpret_cast<const float4 *>(&bs[i][4]);
+    const float4 q2 = *reinterpret_cast<const float4 *>(&bs[i][8]);
+    const float bb[SBP] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    float v0 = t0, v1 = t1;
 #pragma unroll
-    for (int l = 0; l < NB; ++l) v += bs[i][l] * s[l];
-    __stcs(o + (size_t)i * V3, v);
+    for (int l = 0; l < NB; ++l) { v0 += bb[l] * s0[l]; v1 += bb[l] * s1[l]; }
+    if (c0 < V3) __stcs(o + (size_t)i * V3 + c0, v0);
+    if (c1 < V3) __stcs(o + (size_t)i * V3 + c1, v1);
   }
 }
 
@@ -616,7 +630,7 @@ extern "C" int shapy_smplx_forward_shape(const shapy_smplx_t *m, const float *be
   cudaStream_t st = (cudaStream_t)stream;
   const int V3 = d.V * 3;
   if (d.NB == 10) {
-    dim3 grid(ceil_div(V3, 256), ceil_div(B, SB));
+    dim3 grid(ceil_div(V3, 512), ceil_div(B, SB));
     smplx_shape_kernel<10><<<grid, 256, 0, st>>>(d.v_template, d.shapedirs, betas, V3, B, v_shaped);
   } else {
     dim3 grid(ceil_div(V3, 256), B);
