@@ -373,10 +373,10 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo
          (1ull << 46);
 }
 
-// Halo kernel warp roles: warps 0..3 fill the A planes with 16-byte cp.async (zero-filled outside the image;
+// Halo kernel warp roles: warps 0..7 fill the A planes with 16-byte cp.async (zero-filled outside the image;
 // a TMA box with a 16-byte inner row sustains only ~2 B/cycle/SM, measured), warp 0 lane 0 also streams the
-// weights by TMA; warp 4 issues the MMAs; warps 5..12 run the epilogue.
-constexpr int kHaloProd = 4;
+// weights by TMA; warp 8 issues the MMAs; warps 9..16 run the epilogue.
+constexpr int kHaloProd = 8;
 constexpr int kHaloThreads = 32 * (kHaloProd + 1 + kEpiWarps);
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
@@ -569,9 +569,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 5..12)
+    // ===================================================================== epilogue (8 warps after the MMA warp)
     const int q = warp & 3;
-    const int half = (warp - (kHaloProd + 1)) >> 2;
+    const int half = ((warp - (kHaloProd + 1)) >> 2) & 1;
     const int row = q * 32 + lane;
     const int per_img = p.Hb * p.Wp;
     int lt = 0;
@@ -720,6 +720,13 @@ static bool halo_enabled() {
   if (v < 0) { const char *e = getenv("SHAPY_CONV_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+// Measured (profiles/r01_*): with 64-channel k-blocks the halo variant's 16-byte cp.async fill of ~90 KB slices is
+// slower than re-streaming taps through TMA, so those layers stay on the per-tap kernel.
+static int halo_max_kch() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SHAPY_CONV_HALO_MAXKCH"); v = e ? atoi(e) : 32; }
+  return v;
+}
 
 // Chooses the super-tile of the halo-resident kernel by a small traffic / MMA cost model.
 static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, const ActView &out, const ActView *res,
@@ -845,7 +852,7 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
   const int kch = pick_kch(w.cin);
   pl->kch = kch;
   pl->split = split;
-  if (w.ksize == 3 && w.stride == 1 && halo_enabled() && halo_configure(pl, w, in, out, res, relu)) {
+  if (w.ksize == 3 && w.stride == 1 && halo_enabled() && kch <= halo_max_kch() && halo_configure(pl, w, in, out, res, relu)) {
     pl->halo = true;
     return pl;
   }
