@@ -32,6 +32,8 @@ constexpr int KC = 32;  // pose-feature rows staged per chunk
 struct SmplxDev {
   int V, J, NB, NE, NC, F, L, D, rows, K, n_chain, n_levels, ell_w_n, n_extra, n_over;
   float *v_template, *shapedirs /* [NC][3V] */, *posedirs /* [(J-1)*9][3V] */;
+  float *basis;   /* [NC + (J-1)*9][V3p]: shape, expression and pose blend-shape rows, 16-byte aligned rows */
+  int V3p;
   float *J_template /* [3J] */, *J_dirs /* [3J][NC] */;
   int *ell_idx;   /* [W][V] */
   float *ell_w;   /* [W][V] */
@@ -77,7 +79,7 @@ __global__ void decode_rot6d_kernel(const float *__restrict__ raw, int n, float 
 }
 
 // ----------------------------------------------------------------------------------------------
-// Workspace layout (floats): A [B][J][12] | pfT [Kp][Bpad] | lut [B] (int) | reg scratch none
+// Workspace layout (floats): A [B][J][12] | pfT [NC + Kp][Bpad] (blend coefficients, transposed) | lut [B] (int)
 struct PoseArgs {
   SmplxDev m;
   const float *betas, *expr, *rot;
@@ -140,9 +142,11 @@ __global__ void __launch_bounds__(128) smplx_pose_kernel(PoseArgs a) {
     for (int i = t; i < J * 3; i += blockDim.x) a.joints[((size_t)b * m.K) * 3 + i] = G[i / 3][(i % 3) * 4 + 3];
   }
   // pose feature (R[1:] - I), transposed so that a body tile is contiguous
+  // blend coefficients of this body, one row per basis row: [betas | expression | pose feature]
+  if (t < m.NC) a.pfT[(size_t)t * a.Bpad + b] = coef[t];
   for (int k = t; k < a.Kp; k += blockDim.x) {
     int j = 1 + k / 9, e = k % 9;
-    a.pfT[(size_t)k * a.Bpad + b] = R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+    a.pfT[(size_t)(m.NC + k) * a.Bpad + b] = R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
   }
   // dynamic-contour LUT row (lbs.py:30-41, rotation_utils.py:86-92)
   if (t == 0 && m.D > 0) {
@@ -172,21 +176,22 @@ struct VertexArgs {
   float *vertices, *v_shaped;  // either may be null
 };
 
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *src, int src_bytes) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// One tile = 32 vertices (one per lane) x 32 bodies (8 per warp).  All blend-shape rows (shape, expression, pose)
+// are one [rows][V3p] basis; a chunk of 32 rows (96 floats each) and the matching [rows][32 bodies] coefficient
+// block are staged in shared memory with 16-byte cp.async, double buffered, so every constant crosses L2 once
+// per tile and the loads of chunk i+1 overlap the FMAs of chunk i.
 __global__ void __launch_bounds__(128) smplx_vertex_kernel(VertexArgs a) {
   const SmplxDev &m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x;
   const int v0 = blockIdx.x * TV, b0 = blockIdx.y * TB;
-  const int V3 = m.V * 3, c0 = v0 * 3;
-  __shared__ __align__(16) float Ps[KC][TV * 3];
-  __shared__ __align__(16) float pfs[KC][TB];
-  __shared__ float cs[TB][kMaxCoef + 1];
-  // coefficients of this body tile
-  for (int i = t; i < TB * m.NC; i += blockDim.x) {
-    int bl = i / m.NC, l = i % m.NC, b = b0 + bl;
-    float v = 0.f;
-    if (b < a.B) v = l < m.NB ? a.betas[(size_t)b * m.NB + l] : (a.expr ? a.expr[(size_t)b * m.NE + (l - m.NB)] : 0.f);
-    cs[bl][l] = v;
-  }
+  const int c0 = v0 * 3;
+  __shared__ __align__(16) float Ps[2][KC][TV * 3];
+  __shared__ __align__(16) float pfs[2][KC][TB];
   const int v = v0 + lane;
   const bool vok = v < m.V;
   float acc[8][3];
@@ -196,73 +201,66 @@ __global__ void __launch_bounds__(128) smplx_vertex_kernel(VertexArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i][0] = tx; acc[i][1] = ty; acc[i][2] = tz; }
   }
-  __syncthreads();
-  // ---- shape (and expression) blend; shapedirs stored [NC][3V] so a tile row is contiguous
-  for (int l0 = 0; l0 < m.NC; l0 += KC) {
-    int nl = min(KC, m.NC - l0);
-    for (int i = t; i < nl * TV * 3; i += blockDim.x) {
-      int k = i / (TV * 3), c = i % (TV * 3);
-      Ps[k][c] = (c0 + c < V3) ? m.shapedirs[(size_t)(l0 + k) * V3 + c0 + c] : 0.f;
+  // row schedule: [0, NB) shape | [NB, NC) expression (only when given) | [NC, NC + Kp) pose (only for vertices)
+  const bool posed = a.vertices != nullptr;
+  const int n_expr = (a.expr && posed) ? m.NC - m.NB : 0;
+  const int n_rows = m.NB + n_expr + (posed ? a.Kp : 0);
+  auto row_of = [&](int i) { return i < m.NB + n_expr ? i : m.NC + (i - m.NB - n_expr); };
+  // chunk boundaries: the first chunk ends exactly after the NB shape rows (v_shaped snapshot)
+  auto chunk_begin = [&](int ch) { return ch == 0 ? 0 : m.NB + (ch - 1) * KC; };
+  const int n_chunks = 1 + (n_rows > m.NB ? (n_rows - m.NB + KC - 1) / KC : 0);
+  auto load_chunk = [&](int ch, int buf) {
+    const int r0 = chunk_begin(ch), r1 = min(n_rows, ch == 0 ? m.NB : r0 + KC);
+    const int nr = r1 - r0;
+    for (int i = t; i < nr * 24; i += 128) {            // 96 floats = 24 x 16 bytes per row
+      const int k = i / 24, q = i % 24;
+      const int col = c0 + q * 4;
+      const int nb = max(0, min(16, (m.V3p - col) * 4));
+      const float *src = m.basis + (size_t)row_of(r0 + k) * m.V3p + (nb ? col : 0);
+      cp_async16_zfill(&Ps[buf][k][q * 4], src, nb);
+    }
+    for (int i = t; i < nr * 8; i += 128) {             // 32 bodies = 8 x 16 bytes per row
+      const int k = i / 8, q = i % 8;
+      cp_async16_zfill(&pfs[buf][k][q * 4], a.pfT + (size_t)row_of(r0 + k) * a.Bpad + b0 + q * 4, 16);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_chunk(0, 0);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < n_chunks) {
+      load_chunk(ch + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    for (int k = 0; k < nl; ++k) {
-      if (l0 + k == m.NB && a.v_shaped && vok) {
-        // v_shaped = v_template + shapedirs[:, :, :NB] . betas  (body_models.py:763-765)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int b = b0 + warp * 8 + i;
-          if (b < a.B) {
-            float *o = a.v_shaped + ((size_t)b * m.V + v) * 3;
-            o[0] = acc[i][0]; o[1] = acc[i][1]; o[2] = acc[i][2];
-          }
-        }
-      }
-      float px = Ps[k][3 * lane], py = Ps[k][3 * lane + 1], pz = Ps[k][3 * lane + 2];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float f = cs[warp * 8 + i][l0 + k];
-        acc[i][0] += f * px; acc[i][1] += f * py; acc[i][2] += f * pz;
-      }
-    }
-    __syncthreads();
-  }
-  if (m.NC == m.NB && a.v_shaped && vok) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int b = b0 + warp * 8 + i;
-      if (b < a.B) {
-        float *o = a.v_shaped + ((size_t)b * m.V + v) * 3;
-        o[0] = acc[i][0]; o[1] = acc[i][1]; o[2] = acc[i][2];
-      }
-    }
-  }
-  if (!a.vertices) return;
-  // ---- pose blend: acc += pose_feature . posedirs, Kp rows, staged KC at a time
-  for (int k0 = 0; k0 < a.Kp; k0 += KC) {
-    int nk = min(KC, a.Kp - k0);
-    for (int i = t; i < nk * TV * 3; i += blockDim.x) {
-      int k = i / (TV * 3), c = i % (TV * 3);
-      Ps[k][c] = (c0 + c < V3) ? __ldg(m.posedirs + (size_t)(k0 + k) * V3 + c0 + c) : 0.f;
-    }
-    for (int i = t; i < nk * TB; i += blockDim.x) {
-      int k = i / TB, bl = i % TB;
-      pfs[k][bl] = (b0 + bl < a.B) ? a.pfT[(size_t)(k0 + k) * a.Bpad + b0 + bl] : 0.f;
-    }
-    __syncthreads();
+    const int r0 = chunk_begin(ch), nr = min(n_rows, ch == 0 ? m.NB : r0 + KC) - r0;
 #pragma unroll 4
-    for (int k = 0; k < nk; ++k) {
-      float px = Ps[k][3 * lane], py = Ps[k][3 * lane + 1], pz = Ps[k][3 * lane + 2];
-      float4 f0 = *reinterpret_cast<const float4 *>(&pfs[k][warp * 8]);
-      float4 f1 = *reinterpret_cast<const float4 *>(&pfs[k][warp * 8 + 4]);
-      float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    for (int k = 0; k < nr; ++k) {
+      const float px = Ps[buf][k][3 * lane], py = Ps[buf][k][3 * lane + 1], pz = Ps[buf][k][3 * lane + 2];
+      const float4 f0 = *reinterpret_cast<const float4 *>(&pfs[buf][k][warp * 8]);
+      const float4 f1 = *reinterpret_cast<const float4 *>(&pfs[buf][k][warp * 8 + 4]);
+      const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         acc[i][0] += f[i] * px; acc[i][1] += f[i] * py; acc[i][2] += f[i] * pz;
       }
     }
+    if (ch == 0 && a.v_shaped && vok) {
+      // v_shaped = v_template + shapedirs[:, :, :NB] . betas  (body_models.py:763-765)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int b = b0 + warp * 8 + i;
+        if (b < a.B) {
+          float *o = a.v_shaped + ((size_t)b * m.V + v) * 3;
+          o[0] = acc[i][0]; o[1] = acc[i][1]; o[2] = acc[i][2];
+        }
+      }
+    }
     __syncthreads();
   }
-  if (!vok) return;
+  if (!posed || !vok) return;
   // ---- sparse linear blend skinning: out = sum_j w_vj (A_j . [v_posed; 1])
   float out[8][3];
 #pragma unroll
@@ -451,6 +449,15 @@ extern "C" int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t 
   }
   s.shapedirs = upload(m, S, err);
   s.posedirs = upload(m, std::vector<float>(d->posedirs, d->posedirs + (size_t)(J - 1) * 9 * V * 3), err);
+  {
+    // unified blend-shape basis with rows padded to a multiple of 4 floats (16-byte cp.async)
+    const int V3 = V * 3, V3p = (V3 + 3) / 4 * 4, KP = (J - 1) * 9;
+    std::vector<float> basis((size_t)(NC + KP) * V3p, 0.f);
+    for (int l = 0; l < NC; ++l) memcpy(&basis[(size_t)l * V3p], &S[(size_t)l * V3], (size_t)V3 * sizeof(float));
+    for (int k = 0; k < KP; ++k) memcpy(&basis[(size_t)(NC + k) * V3p], d->posedirs + (size_t)k * V3, (size_t)V3 * sizeof(float));
+    s.V3p = V3p;
+    s.basis = upload(m, basis, err);
+  }
   // joint regression contracted with the template and the shape basis (fp64 accumulate)
   std::vector<float> Jt((size_t)J * 3), Jd((size_t)J * 3 * NC);
   for (int j = 0; j < J; ++j) {
@@ -573,7 +580,7 @@ static inline int bpad(int B) { return (B + 31) / 32 * 32; }
 extern "C" size_t shapy_smplx_workspace_bytes(const shapy_smplx_t *m, int B) {
   if (!m || B <= 0) return 0;
   size_t a = align_up((size_t)B * m->d.J * 12 * sizeof(float), 256);
-  size_t p = align_up((size_t)(m->d.J - 1) * 9 * bpad(B) * sizeof(float), 256);
+  size_t p = align_up((size_t)((m->d.J - 1) * 9 + m->d.NC) * bpad(B) * sizeof(float), 256);
   size_t l = align_up((size_t)B * sizeof(int), 256);
   size_t j = align_up((size_t)B * m->d.K * 3 * sizeof(float), 256);
   return a + p + l + j;
@@ -601,7 +608,7 @@ extern "C" int shapy_smplx_forward(const shapy_smplx_t *m, const float *betas, c
   const SmplxDev &d = m->d;
   char *w = (char *)workspace;
   float *A = (float *)w; w += align_up((size_t)B * d.J * 12 * sizeof(float), 256);
-  float *pfT = (float *)w; w += align_up((size_t)(d.J - 1) * 9 * bpad(B) * sizeof(float), 256);
+  float *pfT = (float *)w; w += align_up((size_t)((d.J - 1) * 9 + d.NC) * bpad(B) * sizeof(float), 256);
   int *lut = (int *)w; w += align_up((size_t)B * sizeof(int), 256);
   float *jscratch = (float *)w;
   const int Kp = (n_rot - 1) * 9;

@@ -51,21 +51,33 @@ def make_smplx(seed: int = 2, fixture=None, dtype=torch.float32) -> dict:
     shapedirs_all = torch.randn(V, 3, 20, generator=g) * 5e-3
     posedirs = torch.randn((J - 1) * 9, V * 3, generator=g) * 1e-3
 
+    # Spatially coherent joint regressor and skinning weights (like the real SMPL-X, whose weights are smooth
+    # functions of position): 55 joint "seeds" by farthest-point sampling on the template, every joint regresses
+    # from its 32 nearest vertices, every vertex is skinned to its 4 nearest joints.
+    vt = v_template.double()
+    seeds = [int(((vt - vt.mean(0)) ** 2).sum(1).argmin())]
+    dmin = ((vt - vt[seeds[0]]) ** 2).sum(1)
+    for _ in range(J - 1):
+        seeds.append(int(dmin.argmax()))
+        dmin = torch.minimum(dmin, ((vt - vt[seeds[-1]]) ** 2).sum(1))
+    d2 = ((vt[:, None, :] - vt[seeds][None, :, :]) ** 2).sum(-1)          # (V, J)
+    J_regressor = torch.zeros(J, V)
+    for j in range(J):
+        idx = torch.topk(-d2[:, j], 32).indices
+        J_regressor[j, idx] = torch.softmax(-d2[idx, j] / (2 * 0.03 ** 2), 0).float()
+    near = torch.topk(-d2, 4, dim=1).indices                               # (V, 4)
+    w = torch.softmax(-torch.gather(d2, 1, near) / (2 * 0.08 ** 2), 1).float().clamp_min(1e-4)
+    w = w / w.sum(1, keepdim=True)
+    lbs_weights = torch.zeros(V, J)
+    lbs_weights.scatter_(1, near, w)
+
     def sparse_rows(nrows, nnz):
         R = torch.zeros(nrows, V)
         for r in range(nrows):
             idx = torch.randperm(V, generator=g)[:nnz]
-            w = torch.softmax(torch.randn(nnz, generator=g), 0)
-            R[r, idx] = w
+            w_ = torch.softmax(torch.randn(nnz, generator=g), 0)
+            R[r, idx] = w_
         return R
-
-    J_regressor = sparse_rows(J, 32)
-    # 4 random joints per vertex, Dirichlet(1) weights
-    jidx = torch.stack([torch.randperm(J, generator=g)[:4] for _ in range(V)])
-    w = -torch.log(torch.rand(V, 4, generator=g).clamp_min(1e-6))
-    w = w / w.sum(1, keepdim=True)
-    lbs_weights = torch.zeros(V, J)
-    lbs_weights.scatter_(1, jidx, w)
 
     def dirichlet(*shape):
         x = -torch.log(torch.rand(*shape, 3, generator=g).clamp_min(1e-6))
