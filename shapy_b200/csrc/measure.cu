@@ -17,6 +17,7 @@
 namespace shapy {
 
 constexpr int kMaxPts = 512;
+constexpr int kMaxCand = 4096;  // (face, plane, query triangle) candidates that pass the AABB filter, per body
 
 struct MeasureArgs {
   const float *verts;  // (B,V,3) or null
@@ -67,7 +68,10 @@ __global__ void __launch_bounds__(kMeasThreads) measure_kernel(MeasureArgs a) {
   __shared__ float hs[3];
   __shared__ float lmy[2];
   __shared__ float red[kMeasThreads / 32];
+  __shared__ int cand[kMaxCand];
+  __shared__ int ncand;
   if (t < 3) cnt[t] = 0;
+  if (t == 0) ncand = 0;
   if (t < 5) {
     mmi::Tri tr = load_tri(a, b, a.lm.face_idx[t]);
     // (tri * bc.reshape(3,1)).sum(0): v0*bc0 + v1*bc1 + v2*bc2, y component
@@ -77,6 +81,9 @@ __global__ void __launch_bounds__(kMeasThreads) measure_kernel(MeasureArgs a) {
   __syncthreads();
   const float h0 = hs[0], h1 = hs[1], h2 = hs[2];
   float vol = 0.f;
+  // ---- phase 1: stream all faces once: signed volume + coarse (AABB) filter against the three planes.
+  // Survivors go to a shared-memory queue so that the expensive exact predicates (phase 2) run with one
+  // candidate per thread instead of one diverged lane per warp.
   for (int f = t; f < a.F; f += blockDim.x) {
     mmi::Tri T = load_tri(a, b, f);
     // compute_mass, body_measurements.py:207-214
@@ -89,21 +96,31 @@ __global__ void __launch_bounds__(kMeasThreads) measure_kernel(MeasureArgs a) {
     for (int p = 0; p < 3; ++p) {
       float h = p == 0 ? h0 : (p == 1 ? h1 : h2);
       if (!((h <= tb.hi.y) && (h >= tb.lo.y))) continue;
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        mmi::Tri Q;
-        Q.v0 = make_float3(-1.f, h, -1.f);
-        Q.v1 = q == 0 ? make_float3(1.f, h, -1.f) : make_float3(1.f, h, 1.f);
-        Q.v2 = q == 0 ? make_float3(1.f, h, 1.f) : make_float3(-1.f, h, 1.f);
-        if (!mmi::sat11(Q, T)) continue;
-        float3 b1 = make_float3(0, 0, 0), b2 = b1;
-        mmi::isect_points(Q, T, b1, b2);  // no hit -> barycentrics stay 0 (first-body semantics)
-        int slot = atomicAdd(&cnt[p], 1);
-        if (slot < kMaxPts) {
-          pts[p][slot][0] = T.v0.x * b1.x + T.v1.x * b1.y + T.v2.x * b1.z;
-          pts[p][slot][1] = T.v0.y * b1.x + T.v1.y * b1.y + T.v2.y * b1.z;
-          pts[p][slot][2] = T.v0.z * b1.x + T.v1.z * b1.y + T.v2.z * b1.z;
-        }
+      int slot = atomicAdd(&ncand, 2);
+      if (slot + 1 < kMaxCand) { cand[slot] = (f << 3) | (p << 1); cand[slot + 1] = (f << 3) | (p << 1) | 1; }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: exact SAT + "first ray hit" point selection, one (face, plane, query triangle) per thread
+  {
+    const int n = min(ncand, kMaxCand);
+    if (ncand > kMaxCand && t == 0 && a.status) atomicExch(a.status, 1);
+    for (int i = t; i < n; i += blockDim.x) {
+      const int c = cand[i], f = c >> 3, p = (c >> 1) & 3, q = c & 1;
+      const float h = p == 0 ? h0 : (p == 1 ? h1 : h2);
+      mmi::Tri T = load_tri(a, b, f);
+      mmi::Tri Q;
+      Q.v0 = make_float3(-1.f, h, -1.f);
+      Q.v1 = q == 0 ? make_float3(1.f, h, -1.f) : make_float3(1.f, h, 1.f);
+      Q.v2 = q == 0 ? make_float3(1.f, h, 1.f) : make_float3(-1.f, h, 1.f);
+      if (!mmi::sat11(Q, T)) continue;
+      float3 b1 = make_float3(0, 0, 0), b2 = b1;
+      mmi::isect_points(Q, T, b1, b2);  // no hit -> barycentrics stay 0 (first-body semantics)
+      int slot = atomicAdd(&cnt[p], 1);
+      if (slot < kMaxPts) {
+        pts[p][slot][0] = T.v0.x * b1.x + T.v1.x * b1.y + T.v2.x * b1.z;
+        pts[p][slot][1] = T.v0.y * b1.x + T.v1.y * b1.y + T.v2.y * b1.z;
+        pts[p][slot][2] = T.v0.z * b1.x + T.v1.z * b1.y + T.v2.z * b1.z;
       }
     }
   }
