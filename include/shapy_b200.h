@@ -139,10 +139,10 @@ int shapy_head_forward(const float *feats, int batch, int feat_dim, int param_di
                        size_t workspace_bytes, void *stream);
 
 /* The MLP has no activation, so a stage collapses exactly (in real arithmetic) to p' = p + Mf f + Mp p + c.
- * MfT (F, P) = (W2 W1 W0[:, :F])^T, Mp (P, P) = W2 W1 W0[:, F:], c (P) = W2 (W1 b0 + b1) + b2, contracted by the
- * caller in fp64.  workspace >= B * P * 4 bytes. */
+ * MfT (F, P) = (W2 W1 W0[:, :F])^T, MpT (P, P) = (W2 W1 W0[:, F:])^T, c (P) = W2 (W1 b0 + b1) + b2, contracted by
+ * the caller in fp64.  workspace >= B * P * 4 bytes. */
 int shapy_head_forward_collapsed(const float *feats, int batch, int feat_dim, int param_dim, const float *MfT,
-                                 const float *Mp, const float *c, const float *mean, int num_stages,
+                                 const float *MpT, const float *c, const float *mean, int num_stages,
                                  float *params_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* -------------------------------------------------------------------- HRNet */

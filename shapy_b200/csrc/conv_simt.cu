@@ -131,47 +131,56 @@ int launch_conv_simt(const ConvW &w, const ActView &in, const ActView &out, cons
 __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img, int N, int H, int W,
                                                    const float *__restrict__ wf, const float *__restrict__ bias, int Cout,
                                                    __half *out_hi, __half *out_lo, int ctot, int coff) {
+  // one thread = one output pixel x 16 output channels; the 4 (Cout = 64) threads of a pixel are adjacent lanes, so a
+  // warp writes 8 pixels x 128 contiguous bytes per plane and reads its weights as 4 distinct broadcast LDS.128.
   extern __shared__ __align__(16) float ws[];  // [27][Cout] + bias[Cout]
   for (int i = threadIdx.x; i < 27 * Cout + Cout; i += blockDim.x) ws[i] = i < 27 * Cout ? wf[i] : bias[i - 27 * Cout];
   __syncthreads();
   const int Ho = H / 2, Wo = W / 2;
-  const int groups = Cout / 8;
+  const int groups = Cout / 16;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long pix = idx / groups;
   const int g = (int)(idx % groups);
   if (pix >= (long long)N * Ho * Wo) return;
   const int n = (int)(pix / (Ho * Wo)), r = (int)(pix % (Ho * Wo)), oh = r / Wo, ow = r % Wo;
-  float acc[8];
+  float acc[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = ws[27 * Cout + g * 8 + j];
+  for (int j = 0; j < 16; ++j) acc[j] = ws[27 * Cout + g * 16 + j];
+#pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
-    int ih = oh * 2 + ky - 1;
-    if (ih < 0 || ih >= H) continue;
+    const int ih = oh * 2 + ky - 1;
+#pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      int iw = ow * 2 + kx - 1;
-      if (iw < 0 || iw >= W) continue;
+      const int iw = ow * 2 + kx - 1;
+      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
-        float x = __ldg(img + (((size_t)n * 3 + ci) * H + ih) * W + iw);
-        const float4 *wr = reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * 3 + ci) * Cout + g * 8);
-        const float4 w0 = wr[0], w1 = wr[1];
-        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
-        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+        const float x = ok ? __ldg(img + (((size_t)n * 3 + ci) * H + ih) * W + iw) : 0.f;
+        const float4 *wr = reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * 3 + ci) * Cout + g * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wr[q];
+          acc[4 * q] += x * w4.x; acc[4 * q + 1] += x * w4.y; acc[4 * q + 2] += x * w4.z; acc[4 * q + 3] += x * w4.w;
+        }
       }
     }
   }
-  __align__(16) __half hi[8], lo[8];
+  __align__(16) __half hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) split_store(fmaxf(acc[j], 0.f), hi[j], lo[j]);
-  size_t o = (size_t)pix * ctot + coff + g * 8;
-  *reinterpret_cast<uint4 *>(out_hi + o) = *reinterpret_cast<const uint4 *>(hi);
-  if (out_lo) *reinterpret_cast<uint4 *>(out_lo + o) = *reinterpret_cast<const uint4 *>(lo);
+  for (int j = 0; j < 16; ++j) split_store(fmaxf(acc[j], 0.f), hi[j], lo[j]);
+  const size_t o = (size_t)pix * ctot + coff + g * 16;
+  reinterpret_cast<uint4 *>(out_hi + o)[0] = reinterpret_cast<const uint4 *>(hi)[0];
+  reinterpret_cast<uint4 *>(out_hi + o)[1] = reinterpret_cast<const uint4 *>(hi)[1];
+  if (out_lo) {
+    reinterpret_cast<uint4 *>(out_lo + o)[0] = reinterpret_cast<const uint4 *>(lo)[0];
+    reinterpret_cast<uint4 *>(out_lo + o)[1] = reinterpret_cast<const uint4 *>(lo)[1];
+  }
 }
 
 int launch_stem(const ConvW &w, const float *images, int N, int H, int W, const ActView &out, cudaStream_t st) {
-  SHAPY_REQUIRE(w.cin == 3 && w.ksize == 3 && w.stride == 2 && w.cout % 8 == 0 && w.w_f32, "stem: unsupported conv");
+  SHAPY_REQUIRE(w.cin == 3 && w.ksize == 3 && w.stride == 2 && w.cout % 16 == 0 && w.w_f32, "stem: unsupported conv");
   SHAPY_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: odd input size");
-  long long total = (long long)N * (H / 2) * (W / 2) * (w.cout / 8);
+  long long total = (long long)N * (H / 2) * (W / 2) * (w.cout / 16);
   size_t smem = (size_t)(27 * w.cout + w.cout) * sizeof(float);
   stem_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(images, N, H, W, w.w_f32, w.bias, w.cout, out.hi,
                                                                   out.lo, out.Ctot, out.coff);

@@ -861,7 +861,21 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
   p.TH = std::max(1, std::min(out.H, 128 / p.TW));
   p.TN = (p.TW == out.W && p.TH == out.H) ? std::max(1, std::min(out.N, 128 / (p.TW * p.TH))) : 1;
   p.tiles_w = ceil_div(out.W, p.TW); p.tiles_h = ceil_div(out.H, p.TH); p.tiles_n = ceil_div(out.N, p.TN);
-  p.cin = w.cin; p.cout = w.cout; p.NT = pick_nt(w.cout); p.ksize = w.ksize; p.stride = w.stride;
+  p.cin = w.cin; p.cout = w.cout; p.ksize = w.ksize; p.stride = w.stride;
+  {
+    // cout tile: balance SM utilisation (tiles per 148 CTAs) against the per-MMA operand-read cost (see halo model)
+    const double m_tiles = (double)p.tiles_w * p.tiles_h * p.tiles_n;
+    auto mma_cyc = [](double n) { return std::max((4096.0 + 32.0 * n) / 85.0, n * 0.5); };
+    double best = 1e30;
+    int best_nt = pick_nt(w.cout);
+    for (int nt = 128; nt >= 16; nt -= 16) {
+      if (w.cout % nt) continue;
+      const double per_k = split ? mma_cyc(2.0 * nt) + mma_cyc(nt) : mma_cyc(nt);
+      const double cost = std::ceil(m_tiles * (w.cout / nt) / 148.0) * (per_k * w.ksize * w.ksize * (w.cin / 16) + 400.0 * nt / 16);
+      if (cost < best) { best = cost; best_nt = nt; }
+    }
+    p.NT = best_nt;
+  }
   p.kpt = w.cin / kch;
   p.relu = relu;
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B, N>>3 at 17, M>>4 at 24

@@ -70,25 +70,30 @@ static int gemm(cudaStream_t st, const float *X, int ldx, const float *W, int ld
 // stage is the affine map  p' = p + Mf f + Mp p + c  with Mf = W2 W1 W0[:, :F], Mp = W2 W1 W0[:, F:],
 // c = W2 (W1 b0 + b1) + b2, contracted once at load time in fp64 by the host mirror.
 // g[m][n] = c[n] + sum_k f[m][k] MfT[k][n]: grid (ceil(P/32), B), 4 warps split K, lanes = columns.
-__global__ void __launch_bounds__(128) head_affine_kernel(const float *__restrict__ f, const float *__restrict__ MfT,
+__global__ void __launch_bounds__(512) head_affine_kernel(const float *__restrict__ f, const float *__restrict__ MfT,
                                                           const float *__restrict__ c, int F, int P, float *__restrict__ g) {
-  __shared__ float part[4][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float part[16][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // 16 warps split K, lanes = columns
   const int n = blockIdx.x * 32 + lane, m = blockIdx.y;
-  const int kq = (F + 3) / 4, k0 = warp * kq, k1 = min(F, k0 + kq);
+  const int kq = (F + 15) / 16, k0 = warp * kq, k1 = min(F, k0 + kq);
   const float *fr = f + (size_t)m * F;
   float acc = 0.f;
   if (n < P) {
-#pragma unroll 4
+#pragma unroll 8
     for (int k = k0; k < k1; ++k) acc += __ldg(fr + k) * __ldg(MfT + (size_t)k * P + n);
   }
   part[warp][lane] = acc;
   __syncthreads();
-  if (warp == 0 && n < P) g[(size_t)m * P + n] = c[n] + ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]));
+  if (warp == 0 && n < P) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) s += part[w][lane];
+    g[(size_t)m * P + n] = c[n] + s;
+  }
 }
 
-// all stages of one body: p_{s+1} = p_s + g + Mp p_s
-__global__ void __launch_bounds__(256) head_stages_kernel(const float *__restrict__ g, const float *__restrict__ Mp,
+// all stages of one body: p_{s+1} = p_s + g + Mp p_s   (MpT[j][n] = Mp[n][j], so lanes read consecutive n)
+__global__ void __launch_bounds__(256) head_stages_kernel(const float *__restrict__ g, const float *__restrict__ MpT,
                                                           const float *__restrict__ mean, int P, int B, int num_stages,
                                                           float *__restrict__ out) {
   extern __shared__ float ps[];  // [2][P]
@@ -100,8 +105,8 @@ __global__ void __launch_bounds__(256) head_stages_kernel(const float *__restric
     float *nxt = ps + ((s + 1) & 1) * P;
     for (int n = t; n < P; n += blockDim.x) {
       float acc = 0.f;
-      const float *row = Mp + (size_t)n * P;
-      for (int j = 0; j < P; ++j) acc += row[j] * cur[j];
+#pragma unroll 4
+      for (int j = 0; j < P; ++j) acc += __ldg(MpT + (size_t)j * P + n) * cur[j];
       float v = cur[n] + (g[(size_t)m * P + n] + acc);
       nxt[n] = v;
       out[((size_t)s * B + m) * P + n] = v;
@@ -114,16 +119,16 @@ __global__ void __launch_bounds__(256) head_stages_kernel(const float *__restric
 
 using namespace shapy;
 
-extern "C" int shapy_head_forward_collapsed(const float *feats, int B, int F, int P, const float *MfT, const float *Mp,
+extern "C" int shapy_head_forward_collapsed(const float *feats, int B, int F, int P, const float *MfT, const float *MpT,
                                             const float *c, const float *mean, int num_stages, float *params_out,
                                             void *workspace, size_t workspace_bytes, void *stream) {
-  SHAPY_REQUIRE(feats && MfT && Mp && c && mean && params_out && workspace, "shapy_head_forward_collapsed: null argument");
+  SHAPY_REQUIRE(feats && MfT && MpT && c && mean && params_out && workspace, "shapy_head_forward_collapsed: null argument");
   SHAPY_REQUIRE(B > 0 && num_stages >= 1 && workspace_bytes >= (size_t)B * P * 4, "shapy_head_forward_collapsed: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   float *g = (float *)workspace;
-  head_affine_kernel<<<dim3(ceil_div(P, 32), B), 128, 0, st>>>(feats, MfT, c, F, P, g);
+  head_affine_kernel<<<dim3(ceil_div(P, 32), B), 512, 0, st>>>(feats, MfT, c, F, P, g);
   SHAPY_LAUNCH_CHECK();
-  head_stages_kernel<<<B, 256, 2 * P * sizeof(float), st>>>(g, Mp, mean, P, B, num_stages, params_out);
+  head_stages_kernel<<<B, 256, 2 * P * sizeof(float), st>>>(g, MpT, mean, P, B, num_stages, params_out);
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;
 }

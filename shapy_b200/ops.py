@@ -237,14 +237,14 @@ def head_forward(feats, W0, b0, W1, b1, W2, b2, mean, num_stages=3):
 
 
 def collapse_head(W0, b0, W1, b1, W2, b2, feat_dim):
-    """Contracts the activation-free 3-layer MLP into (MfT, Mp, c) in fp64 (host, once per weight load)."""
+    """Contracts the activation-free 3-layer MLP into (MfT, MpT, c) in fp64 (host, once per weight load)."""
     d = lambda t: t.detach().double().cpu()  # noqa: E731
     W0, b0, W1, b1, W2, b2 = map(d, (W0, b0, W1, b1, W2, b2))
     W21 = W2 @ W1
     Mf = W21 @ W0[:, :feat_dim]
     Mp = W21 @ W0[:, feat_dim:]
     c = W2 @ (W1 @ b0 + b1) + b2
-    return Mf.t().contiguous().float(), Mp.contiguous().float(), c.float()
+    return Mf.t().contiguous().float(), Mp.t().contiguous().float(), c.float()
 
 
 def head_forward_collapsed(feats, MfT, Mp, c, mean, num_stages=3):
