@@ -81,6 +81,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// Programmatic dependent launch: the next kernel of the stream may be launched while this one is still running
+// (its prologue overlaps our tail); it blocks in pdl_wait() until every prior kernel has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
@@ -161,6 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();   // let the next launch start its prologue
+  pdl_wait();                // everything above touched no global memory; inputs of this kernel are now complete
 
   auto tile_coords = [&](int id, int &w0, int &h0, int &n0, int &c_out0) {
     c_out0 = (id % n_tiles) * p.NT; id /= n_tiles;
@@ -420,6 +427,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();   // let the next launch start its prologue
+  pdl_wait();                // everything above touched no global memory; inputs of this kernel are now complete
 
   auto item_coords = [&](int id, int &n0, int &h0, int &c_out0) {
     c_out0 = (id % p.n_tiles) * p.NT; id /= p.n_tiles;
@@ -948,6 +957,30 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
 
 void umma_plan_destroy(UmmaPlan *p) { delete p; }
 
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SHAPY_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <typename Kernel, typename Params>
+static int launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &params) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
+  shapy::count_launch();
+  return SHAPY_OK;
+}
+
 template <int KCH, bool SPLIT>
 static int launch_t(const UmmaPlan *pl, cudaStream_t st) {
   static bool attr_set = false;
@@ -955,9 +988,7 @@ static int launch_t(const UmmaPlan *pl, cudaStream_t st) {
     SHAPY_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<KCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_umma_kernel<KCH, SPLIT><<<pl->grid, kThreads, pl->smem, st>>>(pl->p);
-  SHAPY_LAUNCH_CHECK();
-  return SHAPY_OK;
+  return launch_pdl(conv_umma_kernel<KCH, SPLIT>, pl->grid, kThreads, pl->smem, st, pl->p);
 }
 
 template <int KCH, bool SPLIT>
@@ -995,9 +1026,7 @@ static int launch_halo_t(const UmmaPlan *pl, cudaStream_t st) {
     shapy::count_launch();
     return SHAPY_OK;
   }
-  conv_halo_kernel<KCH, SPLIT><<<pl->grid, kHaloThreads, pl->smem, st>>>(pl->hp);
-  SHAPY_LAUNCH_CHECK();
-  return SHAPY_OK;
+  return launch_pdl(conv_halo_kernel<KCH, SPLIT>, pl->grid, kHaloThreads, pl->smem, st, pl->hp);
 }
 
 int umma_plan_launch(const UmmaPlan *pl, cudaStream_t st) {
