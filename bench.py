@@ -83,6 +83,16 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def conv_traffic(batch: int, mode: int):
+    """DRAM bytes (read + write) of all conv launches of one HRNet forward, from the committed ncu capture
+    profiles/r01_traffic.json (taken at B=64, split mode); None for any other configuration."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if batch != 64 or mode != 1 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get('conv_dram_bytes_per_step')
+
+
 def usable_cores() -> int:
     """Host threads this process may really use: CPU affinity, capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
@@ -321,7 +331,7 @@ def main():
             'gpu_launches': int(launches_per_step * K),
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': conv_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                         'frac': conv_tf / pk['tf_sustained'], 'traffic': None,
+                         'frac': conv_tf / pk['tf_sustained'], 'traffic': conv_traffic(B, args.mode),
                          'kernel': 'conv_umma_kernel (HRNet forward: all 331 convs + fuse + pool)',
                          'ms': hr_ms, 'mma_flops_factor': 3 if args.mode else 1, 'peak_source': pk['source']},
             'roofline_lbs': {'bound': 'hbm', 'achieved': lbs_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
