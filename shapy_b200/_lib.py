@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libshapy_b200.so')
+LIB_PATH = os.environ.get('SHAPY_B200_LIB') or os.path.join(_HERE, 'libshapy_b200.so')   # override: build variants
 
 c_void_p, c_int, c_size_t, c_float_p = C.c_void_p, C.c_int, C.c_size_t, C.c_void_p
 

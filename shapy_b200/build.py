@@ -12,8 +12,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(HERE, '_obj')
-LIB = os.path.join(HERE, 'libshapy_b200.so')
+# experiment variants: SHAPY_BUILD_TAG=x SHAPY_BUILD_DEFS="-DFOO=1" builds libshapy_b200_x.so next to the default
+# library (select it at run time with SHAPY_B200_LIB=<path>); the default build has neither set.
+TAG = os.environ.get('SHAPY_BUILD_TAG', '')
+DEFS = os.environ.get('SHAPY_BUILD_DEFS', '').split()
+OBJ = os.path.join(HERE, '_obj' + ('_' + TAG if TAG else ''))
+LIB = os.path.join(HERE, 'libshapy_b200' + ('_' + TAG if TAG else '') + '.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
@@ -40,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, f)
         obj = os.path.join(OBJ, f[:-3] + '.o')
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr):
-            cmd = [NVCC] + ARCH + COMMON + EXTRA.get(f, []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            cmd = [NVCC] + ARCH + COMMON + DEFS + EXTRA.get(f, []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
             jobs.append((f, cmd))
 
     def run(job):

@@ -29,6 +29,19 @@ struct ConvW {
   int cin = 0, cout = 0, ksize = 0, stride = 0;
 };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one request per 32-byte sector instead of two half-sector
+// ones -- the epilogue's row-per-thread stores are bound by the request rate, not by bytes.  32-byte aligned addresses.
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void *p, const uint4 &a, const uint4 &b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void split_store(float v, __half &hi, __half &lo) {
   v = fminf(fmaxf(v, -65504.f), 65504.f);
   hi = __float2half_rn(v);

@@ -177,11 +177,79 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
   }
 }
 
+// Same convolution, 4 consecutive output pixels x 16 output channels per thread: every weight vector read from shared
+// memory feeds 4 pixels (1 LDS.128 per 16 FMAs instead of per 4; the one-pixel variant above is LDS-bound at ~355 us
+// for 64 x 224 x 224), and the 9 input columns of a row are two aligned LDG.128 plus one scalar.
+__global__ void __launch_bounds__(256, 2) stem4_kernel(const float *__restrict__ img, int N, int H, int W,
+                                                    const float *__restrict__ wf, const float *__restrict__ bias, int Cout,
+                                                    __half *out_hi, __half *out_lo, int ctot, int coff) {
+  extern __shared__ __align__(16) float ws[];  // [27][Cout] + bias[Cout]
+  for (int i = threadIdx.x; i < 27 * Cout + Cout; i += blockDim.x) ws[i] = i < 27 * Cout ? wf[i] : bias[i - 27 * Cout];
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2, Wg = Wo / 4;
+  const int groups = Cout / 16;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pg = idx / groups;
+  const int g = (int)(idx % groups);
+  if (pg >= (long long)N * Ho * Wg) return;
+  const int n = (int)(pg / (Ho * Wg)), r = (int)(pg % (Ho * Wg)), oh = r / Wg, ow0 = (r % Wg) * 4;
+  float acc[4][16];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[p][j] = ws[27 * Cout + g * 16 + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ih = oh * 2 + ky - 1;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const float *row = img + (((size_t)n * 3 + ci) * H + ih) * W + 2 * ow0;   // 32-byte aligned: ow0 % 4 == 0, W % 8 == 0
+      float x[9];
+      x[0] = ow0 > 0 ? __ldg(row - 1) : 0.f;
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(row)), b = __ldg(reinterpret_cast<const float4 *>(row) + 1);
+      x[1] = a.x; x[2] = a.y; x[3] = a.z; x[4] = a.w; x[5] = b.x; x[6] = b.y; x[7] = b.z; x[8] = b.w;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 *wr = reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * 3 + ci) * Cout + g * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wr[q];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float xv = x[2 * p + kx];
+            acc[p][4 * q] += xv * w4.x; acc[p][4 * q + 1] += xv * w4.y;
+            acc[p][4 * q + 2] += xv * w4.z; acc[p][4 * q + 3] += xv * w4.w;
+          }
+        }
+      }
+    }
+  }
+  const size_t pix0 = ((size_t)n * Ho + oh) * Wo + ow0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    __align__(16) __half hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_store(fmaxf(acc[p][j], 0.f), hi[j], lo[j]);
+    const size_t o = (pix0 + p) * ctot + coff + g * 16;   // 32-byte aligned (launch_stem checks ctot, coff, base)
+    stg256(out_hi + o, reinterpret_cast<const uint4 *>(hi)[0], reinterpret_cast<const uint4 *>(hi)[1]);
+    if (out_lo) stg256(out_lo + o, reinterpret_cast<const uint4 *>(lo)[0], reinterpret_cast<const uint4 *>(lo)[1]);
+  }
+}
+
 int launch_stem(const ConvW &w, const float *images, int N, int H, int W, const ActView &out, cudaStream_t st) {
   SHAPY_REQUIRE(w.cin == 3 && w.ksize == 3 && w.stride == 2 && w.cout % 16 == 0 && w.w_f32, "stem: unsupported conv");
   SHAPY_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: odd input size");
-  long long total = (long long)N * (H / 2) * (W / 2) * (w.cout / 16);
   size_t smem = (size_t)(27 * w.cout + w.cout) * sizeof(float);
+  if (W % 8 == 0 && ((uintptr_t)images & 15) == 0 && out.Ctot % 16 == 0 && out.coff % 16 == 0 &&
+      ((uintptr_t)out.hi & 31) == 0 && (!out.lo || ((uintptr_t)out.lo & 31) == 0)) {
+    long long total4 = (long long)N * (H / 2) * (W / 8) * (w.cout / 16);
+    stem4_kernel<<<(unsigned)((total4 + 255) / 256), 256, smem, st>>>(images, N, H, W, w.w_f32, w.bias, w.cout, out.hi,
+                                                                      out.lo, out.Ctot, out.coff);
+    SHAPY_LAUNCH_CHECK();
+    return SHAPY_OK;
+  }
+  long long total = (long long)N * (H / 2) * (W / 2) * (w.cout / 16);
   stem_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(images, N, H, W, w.w_f32, w.bias, w.cout, out.hi,
                                                                   out.lo, out.Ctot, out.coff);
   SHAPY_LAUNCH_CHECK();
@@ -198,38 +266,47 @@ struct FuseParams {
   int out_ctot, out_coff;
 };
 
+// CH = 8: 128-bit accesses; CH = 16: 256-bit accesses (rows 32-byte aligned), half the memory requests.
+template <int CH>
 __global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
-  const int cg = p.C / 8;
+  const int cg = p.C / CH;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long pix = idx / cg;
   const int g = (int)(idx % cg);
   if (pix >= (long long)p.N * p.H * p.W) return;
   const int n = (int)(pix / (p.H * p.W)), r = (int)(pix % (p.H * p.W)), h = r / p.W, w = r % p.W;
-  float acc[8];
+  float acc[CH];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < CH; ++j) acc[j] = 0.f;
   for (int i = 0; i < p.n_in; ++i) {
     const int s = p.shift[i];
     const int Hi = p.H >> s, Wi = p.W >> s;
-    size_t o = (((size_t)n * Hi + (h >> s)) * Wi + (w >> s)) * p.ctot[i] + p.coff[i] + g * 8;
-    uint4 hv = *reinterpret_cast<const uint4 *>(p.hi[i] + o);
-    const __half *hh = reinterpret_cast<const __half *>(&hv);
+    size_t o = (((size_t)n * Hi + (h >> s)) * Wi + (w >> s)) * p.ctot[i] + p.coff[i] + g * CH;
+    uint4 hv[CH / 8], lv[CH / 8];
+    if (CH == 16) ldg256(p.hi[i] + o, hv[0], hv[CH / 8 - 1]); else hv[0] = *reinterpret_cast<const uint4 *>(p.hi[i] + o);
+    const __half *hh = reinterpret_cast<const __half *>(hv);
     if (p.lo[i]) {
-      uint4 lv = *reinterpret_cast<const uint4 *>(p.lo[i] + o);
-      const __half *ll = reinterpret_cast<const __half *>(&lv);
+      if (CH == 16) ldg256(p.lo[i] + o, lv[0], lv[CH / 8 - 1]); else lv[0] = *reinterpret_cast<const uint4 *>(p.lo[i] + o);
+      const __half *ll = reinterpret_cast<const __half *>(lv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]) + __half2float(ll[j]) * kLoInv;
+      for (int j = 0; j < CH; ++j) acc[j] += __half2float(hh[j]) + __half2float(ll[j]) * kLoInv;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += __half2float(hh[j]);
+      for (int j = 0; j < CH; ++j) acc[j] += __half2float(hh[j]);
     }
   }
-  __align__(16) __half hi[8], lo[8];
+  __align__(16) __half hi[CH], lo[CH];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) split_store(p.relu ? fmaxf(acc[j], 0.f) : acc[j], hi[j], lo[j]);
-  size_t o = (size_t)pix * p.out_ctot + p.out_coff + g * 8;
-  *reinterpret_cast<uint4 *>(p.out_hi + o) = *reinterpret_cast<const uint4 *>(hi);
-  if (p.out_lo) *reinterpret_cast<uint4 *>(p.out_lo + o) = *reinterpret_cast<const uint4 *>(lo);
+  for (int j = 0; j < CH; ++j) split_store(p.relu ? fmaxf(acc[j], 0.f) : acc[j], hi[j], lo[j]);
+  size_t o = (size_t)pix * p.out_ctot + p.out_coff + g * CH;
+  const uint4 *h4 = reinterpret_cast<const uint4 *>(hi), *l4 = reinterpret_cast<const uint4 *>(lo);
+  if (CH == 16) {
+    stg256(p.out_hi + o, h4[0], h4[CH / 8 - 1]);
+    if (p.out_lo) stg256(p.out_lo + o, l4[0], l4[CH / 8 - 1]);
+  } else {
+    *reinterpret_cast<uint4 *>(p.out_hi + o) = h4[0];
+    if (p.out_lo) *reinterpret_cast<uint4 *>(p.out_lo + o) = l4[0];
+  }
 }
 
 int launch_fuse(const ActView *ins, const int *shifts, int n_in, const ActView &out, bool relu, cudaStream_t st) {
@@ -243,8 +320,18 @@ int launch_fuse(const ActView *ins, const int *shifts, int n_in, const ActView &
   }
   p.n_in = n_in; p.N = out.N; p.H = out.H; p.W = out.W; p.C = out.C; p.relu = relu;
   p.out_hi = out.hi; p.out_lo = out.lo; p.out_ctot = out.Ctot; p.out_coff = out.coff;
-  long long total = (long long)out.N * out.H * out.W * (out.C / 8);
-  fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  auto al32 = [](const ActView &v) {
+    return v.Ctot % 16 == 0 && v.coff % 16 == 0 && ((uintptr_t)v.hi & 31) == 0 && (!v.lo || ((uintptr_t)v.lo & 31) == 0);
+  };
+  bool wide = out.C % 16 == 0 && al32(out);
+  for (int i = 0; i < n_in; ++i) wide = wide && al32(ins[i]);
+  if (wide) {
+    long long total = (long long)out.N * out.H * out.W * (out.C / 16);
+    fuse_kernel<16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  } else {
+    long long total = (long long)out.N * out.H * out.W * (out.C / 8);
+    fuse_kernel<8><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  }
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;
 }

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "conv.cuh"
 
@@ -71,6 +72,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Same instruction with the two 64-bit descriptors passed as (low, high) 32-bit halves: the issuing lane only ever
+// does 32-bit (uniform-datapath) adds on the low words, the high words are loop constants.
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -107,6 +121,7 @@ struct alignas(64) UmmaParams {
   int G;                         // k-blocks per pipeline stage
   int stages;
   int relu;
+  int vec32;                     // out / residual rows are 32-byte aligned: 256-bit epilogue accesses
   uint32_t idesc, idesc2;        // idesc: N = NT;  idesc2: N = 2 NT ([B_hi | B_lo] in one MMA, split mode)
   uint32_t tmem_cols;
   uint32_t a_bytes, b_bytes, b_stride;  // per k-block: TMA bytes of A / B, smem pitch of a B block
@@ -125,11 +140,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// halves of the same descriptor: low word = start address (16-byte units) | LBO << 16, high word = SBO, version, layout
+template <int KCH>
+__device__ __forceinline__ uint32_t desc_hi_swz() {
+  constexpr uint32_t layout = KCH == 64 ? 2 : (KCH == 32 ? 4 : 6);
+  return (uint32_t)((KCH * 2 * 8) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo_swz(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+
 // Persistent, warp-specialised kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 //   warp 0      TMA producer  (smem ring runs ahead across tile boundaries: no pipeline drain per tile)
 //   warp 1      TMEM allocator + MMA issuer (alternates between two TMEM accumulator buffers)
 //   warps 2..9  epilogue: drains accumulator buffer t & 1 while the MMA warp fills the other one
-constexpr int kEpiWarps = 8;
+#ifndef SHAPY_EPI_WARPS
+#define SHAPY_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = SHAPY_EPI_WARPS;   // multiple of 4: warp w may only read TMEM lanes 32 (w % 4) .. +31
+constexpr int kEpiParts = kEpiWarps / 4;     // warps sharing a lane quarter split the 16-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 template <int KCH, bool SPLIT>
@@ -232,27 +259,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         if (elect_one()) {
           int s_l = s;
           uint32_t ph_l = ph;
+          const uint32_t dhi = desc_hi_swz<KCH>();
+          const uint32_t idesc = p.idesc, idesc2 = p.idesc2;
+          const uint32_t kblk16 = kblk_bytes >> 4, stage16 = stage_bytes >> 4;
+          const uint32_t base16 = desc_lo_swz(smem_base);
+          const int G = p.G;
+          uint32_t first = 0;
 #pragma unroll 1
           for (int it = 0; it < iters; ++it) {
             mbar_wait(full_bar(s_l), ph_l);
             tc_fence_after();
-            const uint32_t sbase = smem_base + stage_bytes * s_l;
-            for (int g = 0; g < p.G; ++g) {
-              const uint32_t kb = sbase + kblk_bytes * g;
-              const uint64_t da0 = make_desc<KCH>(kb), dal0 = make_desc<KCH>(kb + A_BLK);
-              const uint64_t db0 = make_desc<KCH>(kb + A_BLK * (SPLIT ? 2 : 1));
-              const uint32_t first = (it | g) ? 1u : 0u;
+            uint32_t a = base16 + stage16 * s_l;      // low descriptor word of this k-block's A_hi
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+              const uint32_t al = a + (A_BLK >> 4), b = a + ((A_BLK * (SPLIT ? 2 : 1)) >> 4);
 #pragma unroll
-              for (int ks = 0; ks < KCH / 16; ++ks) {
-                const uint64_t ko = (uint64_t)(ks * 2);   // +32 bytes along K, in 16-byte descriptor units
+              for (int ks = 0; ks < KCH / 16; ++ks) {   // +32 bytes along K = +2 descriptor units
                 if (SPLIT) {
                   // [D0 | D1] (+)= A_hi . [B_hi | B_lo]^T  (one N = 2 NT MMA), then D1 += A_lo . B_hi^T
-                  umma_f16(d0, da0 + ko, db0 + ko, p.idesc2, first | (ks ? 1u : 0u));
-                  umma_f16(d1, dal0 + ko, db0 + ko, p.idesc, 1);
+                  umma_f16_lh(d0, a + 2 * ks, dhi, b + 2 * ks, dhi, idesc2, ks ? 1u : first);
+                  umma_f16_lh(d1, al + 2 * ks, dhi, b + 2 * ks, dhi, idesc, 1u);
                 } else {
-                  umma_f16(d0, da0 + ko, db0 + ko, p.idesc, first | (ks ? 1u : 0u));
+                  umma_f16_lh(d0, a + 2 * ks, dhi, b + 2 * ks, dhi, idesc, ks ? 1u : first);
                 }
               }
+              first = 1;
+              a += kblk16;
             }
             umma_commit(empty_bar(s_l));
             if (++s_l == p.stages) { s_l = 0; ph_l ^= 1; }
@@ -266,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   } else {
     // ===================================================================== epilogue (warps 2..9)
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // which alternate 16-column chunks this warp handles
+    const int part = (warp - 2) >> 2;        // which of every kEpiParts 16-column chunks this warp handles
     const int row = q * 32 + lane;           // tile row == TMEM lane
     const int dw = row % p.TW, dh = (row / p.TW) % p.TH, dn = row / (p.TW * p.TH);
     int lt = 0;
@@ -281,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       mbar_wait(acc_full0 + 8u * buf, aph);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-      for (int c = half * 16; c < p.NT; c += 32) {
+      for (int c = part * 16; c < p.NT; c += 16 * kEpiParts) {
         const int co = c_out0 + c;
         // residual rows are fetched before the TMEM load completes so the two latencies overlap
         uint4 rh0 = make_uint4(0, 0, 0, 0), rh1 = rh0, rl0 = rh0, rl1 = rh0;
@@ -289,10 +321,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         if (has_res) {
           const size_t ro = pix * p.res_ctot + p.res_coff + co;
           const uint4 *rh = reinterpret_cast<const uint4 *>(p.res_hi + ro);
-          rh0 = __ldg(rh); rh1 = __ldg(rh + 1);
+          if (p.vec32) ldg256(rh, rh0, rh1); else { rh0 = __ldg(rh); rh1 = __ldg(rh + 1); }
           if (SPLIT && p.res_lo) {
             const uint4 *rl = reinterpret_cast<const uint4 *>(p.res_lo + ro);
-            rl0 = __ldg(rl); rl1 = __ldg(rl + 1);
+            if (p.vec32) ldg256(rl, rl0, rl1); else { rl0 = __ldg(rl); rl1 = __ldg(rl + 1); }
           }
         }
         uint32_t v0[16], v1[16];
@@ -301,11 +333,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         tmem_ld_wait();
         if (!ok) continue;
         float r[16];
+        {
+          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + co);   // co % 16 == 0: 64-byte aligned
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bq = __ldg(b4 + q4);
+            r[4 * q4] = bq.x; r[4 * q4 + 1] = bq.y; r[4 * q4 + 2] = bq.z; r[4 * q4 + 3] = bq.w;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float x = __uint_as_float(v0[j]);
           if (SPLIT) x += __uint_as_float(v1[j]) * kLoInv;
-          r[j] = x + __ldg(p.bias + co + j);
+          r[j] += x;
         }
         if (has_res) {
           const __half *hh0 = reinterpret_cast<const __half *>(&rh0), *hh1 = reinterpret_cast<const __half *>(&rh1);
@@ -320,13 +360,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) split_store(p.relu ? fmaxf(r[j], 0.f) : r[j], hi[j], lo[j]);
         const size_t oo = pix * p.out_ctot + p.out_coff + co;
+        const uint4 *hv = reinterpret_cast<const uint4 *>(hi), *lv = reinterpret_cast<const uint4 *>(lo);
         uint4 *oh4 = reinterpret_cast<uint4 *>(p.out_hi + oo);
-        oh4[0] = reinterpret_cast<const uint4 *>(hi)[0];
-        oh4[1] = reinterpret_cast<const uint4 *>(hi)[1];
+        if (p.vec32) stg256(oh4, hv[0], hv[1]); else { oh4[0] = hv[0]; oh4[1] = hv[1]; }
         if (SPLIT && p.out_lo) {
           uint4 *ol4 = reinterpret_cast<uint4 *>(p.out_lo + oo);
-          ol4[0] = reinterpret_cast<const uint4 *>(lo)[0];
-          ol4[1] = reinterpret_cast<const uint4 *>(lo)[1];
+          if (p.vec32) stg256(ol4, lv[0], lv[1]); else { ol4[0] = lv[0]; ol4[1] = lv[1]; }
         }
       }
       // this warp is done reading the buffer: hand it back to the MMA warp
@@ -361,40 +400,33 @@ struct alignas(64) HaloParams {
   CUtensorMap b_hi, b_lo;  // (cin, cout, 9) swizzled, box (KCH, NT, 1)
   int N, H, W;
   int Wp, Hb, TN, R, bands, n_super, MT;
-  int cin, cout, NT, n_tiles, ncg, bstages, acc_bufs, b_resident;
-  uint32_t PS, a_slice_bytes, a_tx, b_bytes, b_stride;
+  int cin, cout, NT, n_tiles, ncg, bstages, acc_bufs, b_resident, n_iss;
+  int row_sched;    // 1: each CTA owns a contiguous range of the N*H output rows, walked in chunks of <= R rows
+  int a_baseoff;    // 1: put (start >> 7) & 7 into the descriptor's base-offset field for row-shifted starts
+  uint32_t part_bytes;   // offset of the lo part inside an A slice
+  uint32_t a_slice_bytes, a_tx, b_bytes, b_stride;
   uint32_t idesc, idesc2;
   int relu;
+  int vec32;             // out / residual rows are 32-byte aligned: 256-bit epilogue accesses
   const float *bias;
   __half *out_hi, *out_lo;
   int out_ctot, out_coff;
   const __half *res_hi, *res_lo;
   int res_ctot, res_coff;
-  const __half *in_hi, *in_lo;   // NHWC activation planes (cp.async producers)
-  int in_ctot, in_coff;
   unsigned long long *dbg;       // optional [gridDim.x][16] phase cycle counters (SHAPY_CONV_PHASES=1)
+  int dbg_flags;                 // phases mode only: 1 skip the A fills, 2 skip the epilogue work, 4 skip the MMAs
 };
 
-__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) |
-         (1ull << 46);
-}
-
-// Halo kernel warp roles: warps 0..7 fill the A planes with 16-byte cp.async (zero-filled outside the image;
-// a TMA box with a 16-byte inner row sustains only ~2 B/cycle/SM, measured), warp 0 lane 0 also streams the
-// weights by TMA; warp 8 issues the MMAs; warps 9..16 run the epilogue.
-constexpr int kHaloProd = 8;
-constexpr int kHaloThreads = 32 * (kHaloProd + 1 + kEpiWarps);
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
+// Halo kernel warp roles: warp 0 = A-slice TMA producer, warp 1 = weight TMA producer, warps 2..3 = MMA issuers
+// (m-tiles dealt round-robin), then kEpiWarps epilogue warps.
+constexpr int kHaloProd = 2;
+constexpr int kHaloIssue = 2;   // MMA-issuing warps: m-tiles are dealt round-robin, each warp owns its accumulators
+constexpr int kHaloThreads = 32 * (kHaloProd + kHaloIssue + kEpiWarps);
 
 template <int KCH, bool SPLIT>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int PARTS = SPLIT ? 2 : 1;
-  constexpr int PLANES = KCH / 8;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;                                  // 2 slices
   const uint32_t b_base = a_base + 2u * p.a_slice_bytes;              // ring of bstages x PARTS blocks
@@ -409,12 +441,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const uint32_t tmem_slot = acc_empty0 + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = p.n_super * p.n_tiles;
+  unsigned long long g_entry = 0;
+  long long c_entry = 0;
+  if (p.dbg && threadIdx.x == 0) { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_entry)); c_entry = clock64(); }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.bstages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < p.bstages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), p.n_iss); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(a_full0 + 8u * i, 32 * kHaloProd); mbar_init(a_empty0 + 8u * i, 1);
-      mbar_init(acc_full0 + 8u * i, 1); mbar_init(acc_empty0 + 8u * i, kEpiWarps);
+      mbar_init(a_full0 + 8u * i, 1); mbar_init(a_empty0 + 8u * i, p.n_iss);
+      mbar_init(acc_full0 + 8u * i, p.n_iss); mbar_init(acc_empty0 + 8u * i, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -429,6 +464,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_launch_dependents();   // let the next launch start its prologue
   pdl_wait();                // everything above touched no global memory; inputs of this kernel are now complete
+  if (p.dbg && threadIdx.x == 0) {
+    p.dbg[blockIdx.x * 16 + 8] = (unsigned long long)(clock64() - c_entry);   // prologue cycles
+    p.dbg[blockIdx.x * 16 + 9] = g_entry;                                     // ns timestamp at entry
+  }
 
   auto item_coords = [&](int id, int &n0, int &h0, int &c_out0) {
     c_out0 = (id % p.n_tiles) * p.NT; id /= p.n_tiles;
@@ -436,181 +475,252 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     n0 = id * p.TN;
   };
   const uint32_t acc_cols = (uint32_t)p.NT * PARTS;
+  // Work items.  Default: ids blockIdx.x, +gridDim.x, ... over (super-tile, cout tile).  Row scheduling (band mode with
+  // one cout tile): CTA b owns output rows [b T / G, (b + 1) T / G) of the T = N * H rows and walks them in chunks of
+  // at most R rows that do not cross an image boundary; 896 equal items on 148 SMs are 7 waves of 6.05, the row
+  // ranges differ by one row at most.
+  struct HaloItem { long long g, hi; int id, rows; };
+  auto item_begin = [&]() {
+    HaloItem it;
+    it.id = blockIdx.x; it.rows = 0; it.g = 0; it.hi = 0;
+    if (p.row_sched) {
+      const long long T = (long long)p.N * p.H;
+      it.g = T * blockIdx.x / gridDim.x;
+      it.hi = T * (blockIdx.x + 1) / gridDim.x;
+    }
+    return it;
+  };
+  auto item_valid = [&](const HaloItem &it) { return p.row_sched ? it.g < it.hi : it.id < total_items; };
+  auto item_get = [&](HaloItem &it, int &n0, int &h0, int &c_out0, int &rows) {
+    if (p.row_sched) {
+      n0 = (int)(it.g / p.H); h0 = (int)(it.g - (long long)n0 * p.H); c_out0 = 0;
+      rows = min(min(p.R, p.H - h0), (int)(it.hi - it.g));
+    } else {
+      item_coords(it.id, n0, h0, c_out0);
+      rows = p.R;
+    }
+    it.rows = rows;
+  };
+  auto item_next = [&](HaloItem &it) { it.g += it.rows; it.id += gridDim.x; };
 
   if (warp < kHaloProd) {
     // ===================================================================== producers
-    const int pt = threadIdx.x;                      // 0 .. 32 * kHaloProd - 1
-    const bool b_thread = pt == 0;
-    int bs = 0, slice = 0;
-    uint32_t bph = 0, aph = 0;
-    if (b_thread && p.b_resident) {
-      // all 9 x ncg weight blocks of the (single) cout tile stay in shared memory for the whole kernel
-      mbar_expect_tx(b_full(0), p.b_bytes * PARTS * 9u * p.ncg);
-      for (int cg = 0; cg < p.ncg; ++cg)
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t bb = b_base + b_stage_bytes * (cg * 9 + tap);
-          tma_load_3d(bb, &p.b_hi, b_full(0), cg * KCH, 0, tap);
-          if (SPLIT) tma_load_3d(bb + p.b_bytes, &p.b_lo, b_full(0), cg * KCH, 0, tap);
-        }
-    }
-    const int per_img = p.Hb * p.Wp;
-    const int P = p.TN * per_img;
-    constexpr int PAIRS = KCH / 16;                  // 16 channels = one 32-byte sector = two planes
-    for (int id = blockIdx.x; id < total_items; id += gridDim.x) {
-      int n0, h0, c_out0;
-      item_coords(id, n0, h0, c_out0);
-      for (int cg = 0; cg < p.ncg; ++cg) {
-        long long t0 = clock64();
-        mbar_wait(a_empty0 + 8u * slice, aph ^ 1);
-        long long t1 = clock64();
-        const uint32_t sb = a_base + slice * p.a_slice_bytes;
-        for (int idx = pt; idx < P * PAIRS; idx += 32 * kHaloProd) {
-          const int pp = idx / P, pos = idx - pp * P;
-          const int n = pos / per_img, rem = pos - n * per_img, hr = rem / p.Wp, hc = rem - hr * p.Wp;
-          const int ih = h0 - 1 + hr, iw = hc - 1, in_n = n0 + n;
-          const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && in_n < p.N;
-          const size_t off = ok ? ((((size_t)in_n * p.H + ih) * p.W + iw) * p.in_ctot + p.in_coff + cg * KCH + pp * 16) : 0;
-          const uint32_t nbytes = ok ? 16u : 0u;
-          const uint32_t d = sb + (2 * pp) * p.PS + (uint32_t)pos * 16u;
-          cp_async16(d, p.in_hi + off, nbytes);
-          cp_async16(d + p.PS, p.in_hi + off + 8, nbytes);
-          if (SPLIT) {
-            cp_async16(d + PLANES * p.PS, p.in_lo + off, nbytes);
-            cp_async16(d + (PLANES + 1) * p.PS, p.in_lo + off + 8, nbytes);
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05 (async proxy) reads
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full0 + 8u * slice) : "memory");
-        if (p.dbg && pt == 32) { long long t2 = clock64(); atomicAdd(p.dbg + blockIdx.x * 16 + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.dbg + blockIdx.x * 16 + 1, (unsigned long long)(t2 - t1)); }
-        if (++slice == 2) { slice = 0; aph ^= 1; }
-        if (b_thread && !p.b_resident) {
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(b_empty(bs), bph ^ 1);
-            mbar_expect_tx(b_full(bs), p.b_bytes * PARTS);
-            const uint32_t bb = b_base + b_stage_bytes * bs;
-            tma_load_3d(bb, &p.b_hi, b_full(bs), cg * KCH, c_out0, tap);
-            if (SPLIT) tma_load_3d(bb + p.b_bytes, &p.b_lo, b_full(bs), cg * KCH, c_out0, tap);
-            if (++bs == p.bstages) { bs = 0; bph ^= 1; }
+    // warp 0: one elected lane loads each A slice (the band of KCH channels with its halo; out-of-image rows and
+    // columns are zero-filled by the TMA unit = the padding) as two boxes; warp 1: the weight blocks.
+    if (warp == 0) {
+      if (elect_one()) {
+        int slice = 0;
+        uint32_t aph = 0;
+        for (HaloItem it = item_begin(); item_valid(it); item_next(it)) {
+          int n0, h0, c_out0, rows;
+          item_get(it, n0, h0, c_out0, rows);
+          for (int cg = 0; cg < p.ncg; ++cg) {
+            long long t0 = clock64();
+            mbar_wait(a_empty0 + 8u * slice, aph ^ 1);
+            long long t1 = clock64();
+            const uint32_t sb = a_base + slice * p.a_slice_bytes, fb = a_full0 + 8u * slice;
+            if (p.dbg_flags & 1) {
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+            } else {
+              mbar_expect_tx(fb, p.a_tx);
+              tma_load_4d(sb, &p.a_hi, fb, cg * KCH, -1, h0 - 1, n0);
+              if (SPLIT) tma_load_4d(sb + p.part_bytes, &p.a_lo, fb, cg * KCH, -1, h0 - 1, n0);
+            }
+            if (p.dbg) { long long t2 = clock64(); atomicAdd(p.dbg + blockIdx.x * 16 + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.dbg + blockIdx.x * 16 + 1, (unsigned long long)(t2 - t1)); }
+            if (++slice == 2) { slice = 0; aph ^= 1; }
           }
         }
       }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (elect_one()) {
+        if (p.b_resident) {
+          mbar_expect_tx(b_full(0), p.b_bytes * PARTS * 9u * p.ncg);
+          for (int cg = 0; cg < p.ncg; ++cg)
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t bb = b_base + b_stage_bytes * (cg * 9 + tap);
+              tma_load_3d(bb, &p.b_hi, b_full(0), cg * KCH, 0, tap);
+              if (SPLIT) tma_load_3d(bb + p.b_bytes, &p.b_lo, b_full(0), cg * KCH, 0, tap);
+            }
+        } else {
+          int bs = 0;
+          uint32_t bph = 0;
+          for (HaloItem it = item_begin(); item_valid(it); item_next(it)) {
+            int n0, h0, c_out0, rows;
+            item_get(it, n0, h0, c_out0, rows);
+            for (int cg = 0; cg < p.ncg; ++cg)
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(b_empty(bs), bph ^ 1);
+                mbar_expect_tx(b_full(bs), p.b_bytes * PARTS);
+                const uint32_t bb = b_base + b_stage_bytes * bs;
+                tma_load_3d(bb, &p.b_hi, b_full(bs), cg * KCH, c_out0, tap);
+                if (SPLIT) tma_load_3d(bb + p.b_bytes, &p.b_lo, b_full(bs), cg * KCH, c_out0, tap);
+                if (++bs == p.bstages) { bs = 0; bph ^= 1; }
+              }
+          }
+        }
+      }
+      __syncwarp();
     }
-  } else if (warp == kHaloProd) {
-    // ===================================================================== MMA issuer
-    {
+  } else if (warp < kHaloProd + kHaloIssue) {
+    // ===================================================================== MMA issuers
+    // Issuer w handles m-tiles w, w + n_iss, ...: a single thread sustains only one tcgen05.mma per ~70 cycles once
+    // its descriptor arithmetic is added, so two warps on two schedulers feed the tensor pipe.  Every accumulator is
+    // owned by one warp (deterministic summation order); each warp's tcgen05.commit covers its own MMAs.
+    const int iw = warp - kHaloProd;
+    if (iw < p.n_iss) {
       int bs = 0, slice = 0, lt = 0;
       uint32_t bph = 0, aph = 0;
       if (p.b_resident) mbar_wait(b_full(0), 0);
-      const uint64_t lbo_sbo = ((uint64_t)((p.PS >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-      const uint32_t ps16 = p.PS >> 4;
-      for (int id = blockIdx.x; id < total_items; id += gridDim.x, ++lt) {
+      // Descriptor low words are advanced with 32-bit adds only; everything else is hoisted here.  (Measured with
+      // SHAPY_CONV_DBGFLAGS=7: the previous per-tap 64-bit descriptor set-up cost ~250 cycles per tap and made the
+      // whole kernel issue-bound.)
+      const uint32_t b_hi32 = desc_hi_swz<KCH>();
+      // A operand: K-major swizzled rows of KCH channels ([position][KCH], one TMA box per part); a tap or an m-tile is
+      // a whole-row shift of the descriptor start address (the swizzle is a function of the absolute shared-memory
+      // address, so any row offset is legal with base offset 0 -- verified on hardware against the oracle).
+      const uint32_t a_hi32 = desc_hi_swz<KCH>();
+      const uint32_t lo_off = p.part_bytes >> 4;
+      const uint32_t ks_step = 2u;
+      const uint32_t row_u = (uint32_t)(KCH / 8);                                    // descriptor units (16 B) per position
+      const uint32_t a0_16 = desc_lo_swz(a_base);
+      const bool baseoff = p.a_baseoff != 0;
+      const uint32_t a_slice16 = p.a_slice_bytes >> 4;
+      const uint32_t b0_16 = desc_lo_swz(b_base), bst16 = b_stage_bytes >> 4;
+      const uint32_t idesc = p.idesc, idesc2 = p.idesc2, NT = p.NT, wp = p.Wp;
+      const int MT = p.MT, ncg = p.ncg, bstages = p.bstages;
+      const uint32_t m_a = (uint32_t)iw * 128u * row_u, m_d = (uint32_t)iw * acc_cols;
+      const uint32_t st_a = (uint32_t)p.n_iss * 128u * row_u, st_d = (uint32_t)p.n_iss * acc_cols;
+      const bool rec = p.dbg && lane == 0 && iw == 0;
+      const bool no_mma = (p.dbg_flags & 4) != 0;
+      // one tap: MT m-tiles x KCH/16 k-steps x (2 | 1) MMAs; at / bt = low descriptor words of the tap's A / B block.
+      // MTC > 0: the m loop is unrolled at compile time (every operand becomes base + immediate); 0: runtime loop.
+      int mt_rt = 0;   // m-tile count of the runtime-loop variant (MTC == 0)
+      auto issue_tap = [&](auto mtc, uint32_t at, uint32_t a_hi_t, uint32_t bt, uint32_t d, uint32_t acc0) {
+        constexpr int MTC = decltype(mtc)::value;
+        auto one = [&](uint32_t a_m, uint32_t d_m) {
+#pragma unroll
+          for (int ks = 0; ks < KCH / 16; ++ks) {
+            if (SPLIT) {
+              umma_f16_lh(d_m, a_m + ks * ks_step, a_hi_t, bt + 2 * ks, b_hi32, idesc2, ks ? 1u : acc0);        // [D0|D1] (+)= A_hi [B_hi|B_lo]^T
+              umma_f16_lh(d_m + NT, a_m + ks * ks_step + lo_off, a_hi_t, bt + 2 * ks, b_hi32, idesc, 1u);       // D1 += A_lo B_hi^T
+            } else {
+              umma_f16_lh(d_m, a_m + ks * ks_step, a_hi_t, bt + 2 * ks, b_hi32, idesc, ks ? 1u : acc0);
+            }
+          }
+        };
+        if (no_mma) return;
+        if constexpr (MTC > 0) {
+#pragma unroll
+          for (int m = 0; m < MTC; ++m) one(at + m * st_a, d + m * st_d);   // 128 rows x 16 B = 128 descriptor units per m-tile
+        } else {
+#pragma unroll 1
+          for (int m = 0; m < mt_rt; ++m) { one(at, d); at += st_a; d += st_d; }
+        }
+      };
+      // all 9 taps of one channel group (the elected lane only)
+      // per tap: start shift in descriptor units, and the high word (base offset = 128-byte line of the start, mod 8)
+      auto tap_shift = [&](int tap) { return ((uint32_t)(tap / 3) * wp + (uint32_t)(tap % 3)) * row_u; };
+      auto tap_hi = [&](int tap) {
+        const uint32_t line = (tap_shift(tap) << 4) >> 7;
+        return baseoff ? (a_hi32 | ((line & 7u) << 17)) : a_hi32;
+      };
+      auto issue_cg = [&](auto mtc, int cg, uint32_t as, uint32_t dbase, int bs_l, uint32_t bph_l) {
+        if (p.b_resident) {
+          // weights are resident: the taps go out back to back
+          const uint32_t bt0 = b0_16 + (uint32_t)(cg * 9) * bst16;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            issue_tap(mtc, as + tap_shift(tap), tap_hi(tap), bt0 + tap * bst16, dbase, (tap | cg) ? 1u : 0u);
+        } else {
+          // streamed weights: the elected lane also waits for each weight block (a per-tap elect + __syncwarp
+          // costs ~150 cycles per tap)
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_full(bs_l), bph_l);
+            tc_fence_after();
+            issue_tap(mtc, as + tap_shift(tap), tap_hi(tap), b0_16 + bs_l * bst16, dbase, (tap | cg) ? 1u : 0u);
+            umma_commit(b_empty(bs_l));
+            if (++bs_l == bstages) { bs_l = 0; bph_l ^= 1; }
+          }
+        }
+      };
+      for (HaloItem it = item_begin(); item_valid(it); item_next(it), ++lt) {
+        int n0_, h0_, c0_, rows;
+        item_get(it, n0_, h0_, c0_, rows);
+        // m-tiles this item really needs (row scheduling hands out partial chunks), and this warp's share of them
+        const int mt_item = p.row_sched ? ((rows - 1) * (int)wp + p.W + 127) / 128 : MT;
+        const int mt_w = (mt_item - iw + p.n_iss - 1) / p.n_iss;
         const int buf = p.acc_bufs == 2 ? (lt & 1) : 0;
         const uint32_t cph = p.acc_bufs == 2 ? ((lt >> 1) & 1) : (lt & 1);
         long long m0 = clock64();
         mbar_wait(acc_empty0 + 8u * buf, cph ^ 1);
         long long m1 = clock64();
-        if (p.dbg && lane == 0) atomicAdd(p.dbg + blockIdx.x * 16 + 2, (unsigned long long)(m1 - m0));
+        if (rec) atomicAdd(p.dbg + blockIdx.x * 16 + 2, (unsigned long long)(m1 - m0));
         tc_fence_after();
-        const uint32_t dbase = tmem_base + buf * 256u;
-        for (int cg = 0; cg < p.ncg; ++cg) {
+        const uint32_t dbase = tmem_base + buf * 256u + m_d;
+        for (int cg = 0; cg < ncg; ++cg) {
           long long m2 = clock64();
           mbar_wait(a_full0 + 8u * slice, aph);
-          if (p.dbg && lane == 0) atomicAdd(p.dbg + blockIdx.x * 16 + 3, (unsigned long long)(clock64() - m2));
-          const uint32_t sa = a_base + slice * p.a_slice_bytes;
-          // one (tap) step: MT x KCH/16 k-steps x (2 | 1) MMAs
-          auto issue_tap = [&](int tap, uint32_t bb) {
-            const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 16u;
-            const uint64_t db0 = make_desc<KCH>(bb);
-            // no-swizzle A descriptor: start address in 16-byte units in the low 14 bits
-            const uint64_t da_base = lbo_sbo | (uint64_t)(((sa + shift) & 0x3FFFF) >> 4);
-            const uint32_t first = (cg | tap) ? 1u : 0u;
-            for (int m = 0; m < p.MT; ++m) {
-              const uint32_t d0 = dbase + m * acc_cols, d1 = d0 + p.NT;
-              const uint64_t dam = da_base + (uint64_t)(m * 128);   // 128 rows x 16 B = 128 descriptor units
-#pragma unroll
-              for (int ks = 0; ks < KCH / 16; ++ks) {
-                const uint64_t da = dam + (uint64_t)(2 * ks) * ps16;
-                const uint64_t ko = (uint64_t)(ks * 2);
-                if (SPLIT) {
-                  umma_f16(d0, da, db0 + ko, p.idesc2, first | (ks ? 1u : 0u));      // [D0 | D1] (+)= A_hi . [B_hi | B_lo]^T
-                  umma_f16(d1, da + (uint64_t)PLANES * ps16, db0 + ko, p.idesc, 1);  // D1 += A_lo . B_hi^T
-                } else {
-                  umma_f16(d0, da, db0 + ko, p.idesc, first | (ks ? 1u : 0u));
-                }
-              }
+          if (rec) atomicAdd(p.dbg + blockIdx.x * 16 + 3, (unsigned long long)(clock64() - m2));
+          tc_fence_after();
+          const uint32_t as = a0_16 + slice * a_slice16 + m_a;
+          if (elect_one()) {
+            mt_rt = mt_w;
+            switch (mt_w) {
+              case 1: issue_cg(std::integral_constant<int, 1>{}, cg, as, dbase, bs, bph); break;
+              case 2: issue_cg(std::integral_constant<int, 2>{}, cg, as, dbase, bs, bph); break;
+              case 3: issue_cg(std::integral_constant<int, 3>{}, cg, as, dbase, bs, bph); break;
+              case 4: issue_cg(std::integral_constant<int, 4>{}, cg, as, dbase, bs, bph); break;
+              // runtime loop; also mt_w == 0 (a partial chunk leaves this warp no m-tile): the weight-block waits and all
+              // commits still happen, so the barrier phases stay in step
+              default: issue_cg(std::integral_constant<int, 0>{}, cg, as, dbase, bs, bph); break;
             }
-          };
-          if (p.b_resident) {
-            // weights are resident: all 9 taps of this channel group are issued by one elected lane in one go
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll 1
-              for (int tap = 0; tap < 9; ++tap) issue_tap(tap, b_base + b_stage_bytes * (cg * 9 + tap));
-              umma_commit(a_empty0 + 8u * slice);
-              if (cg == p.ncg - 1) umma_commit(acc_full0 + 8u * buf);
-            }
-            __syncwarp();
-          } else {
-            // streamed weights: the elected lane also waits for each weight block, so the whole channel group
-            // is issued from one uniform region (a per-tap elect + __syncwarp costs ~150 cycles per tap)
-            if (elect_one()) {
-              int bs_l = bs;
-              uint32_t bph_l = bph;
-#pragma unroll 1
-              for (int tap = 0; tap < 9; ++tap) {
-                mbar_wait(b_full(bs_l), bph_l);
-                tc_fence_after();
-                issue_tap(tap, b_base + b_stage_bytes * bs_l);
-                umma_commit(b_empty(bs_l));
-                if (++bs_l == p.bstages) { bs_l = 0; bph_l ^= 1; }
-              }
-              umma_commit(a_empty0 + 8u * slice);
-              if (cg == p.ncg - 1) umma_commit(acc_full0 + 8u * buf);
-            }
-            __syncwarp();
-            for (int tap = 0; tap < 9; ++tap) { if (++bs == p.bstages) { bs = 0; bph ^= 1; } }
+            umma_commit(a_empty0 + 8u * slice);
+            if (cg == ncg - 1) umma_commit(acc_full0 + 8u * buf);
           }
+          __syncwarp();
+          if (!p.b_resident) { bs += 9; while (bs >= bstages) { bs -= bstages; bph ^= 1; } }
           if (++slice == 2) { slice = 0; aph ^= 1; }
         }
-        if (p.dbg && lane == 0) atomicAdd(p.dbg + blockIdx.x * 16 + 4, (unsigned long long)(clock64() - m1));
+        if (rec) atomicAdd(p.dbg + blockIdx.x * 16 + 4, (unsigned long long)(clock64() - m1));
       }
     }
   } else {
-    // ===================================================================== epilogue (8 warps after the MMA warp)
+    // ===================================================================== epilogue (8 warps after the MMA warps)
     const int q = warp & 3;
-    const int half = ((warp - (kHaloProd + 1)) >> 2) & 1;
+    const int part = (warp - (kHaloProd + kHaloIssue)) >> 2;
     const int row = q * 32 + lane;
     const int per_img = p.Hb * p.Wp;
     int lt = 0;
-    for (int id = blockIdx.x; id < total_items; id += gridDim.x, ++lt) {
-      int n0, h0, c_out0;
-      item_coords(id, n0, h0, c_out0);
+    for (HaloItem it = item_begin(); item_valid(it); item_next(it), ++lt) {
+      int n0, h0, c_out0, rows;
+      item_get(it, n0, h0, c_out0, rows);
+      const int mt_item = p.row_sched ? ((rows - 1) * p.Wp + p.W + 127) / 128 : p.MT;
       const int buf = p.acc_bufs == 2 ? (lt & 1) : 0;
       const uint32_t cph = p.acc_bufs == 2 ? ((lt >> 1) & 1) : (lt & 1);
       long long e0 = clock64();
       mbar_wait(acc_full0 + 8u * buf, cph);
       long long e1 = clock64();
       tc_fence_after();
-      for (int m = 0; m < p.MT; ++m) {
+      for (int m = 0; m < ((p.dbg_flags & 2) ? 0 : mt_item); ++m) {
         const int o = m * 128 + row;
         const int n = o / per_img, rem = o % per_img, rr = rem / p.Wp, cc = rem % p.Wp;
         const int oh = h0 + rr, on = n0 + n;
-        const bool ok = n < p.TN && rr < p.R && cc < p.W && oh < p.H && on < p.N;
+        const bool ok = n < p.TN && rr < rows && cc < p.W && oh < p.H && on < p.N;
         const size_t pix = ((size_t)on * p.H + oh) * p.W + cc;
         const uint32_t lane_addr = tmem_base + buf * 256u + m * acc_cols + ((uint32_t)(q * 32) << 16);
-        for (int c = half * 16; c < p.NT; c += 32) {
+        for (int c = part * 16; c < p.NT; c += 16 * kEpiParts) {
           const int co = c_out0 + c;
           uint4 rh0 = make_uint4(0, 0, 0, 0), rh1 = rh0, rl0 = rh0, rl1 = rh0;
           const bool has_res = ok && p.res_hi != nullptr;
           if (has_res) {
             const size_t ro = pix * p.res_ctot + p.res_coff + co;
             const uint4 *rh = reinterpret_cast<const uint4 *>(p.res_hi + ro);
-            rh0 = __ldg(rh); rh1 = __ldg(rh + 1);
+            if (p.vec32) ldg256(rh, rh0, rh1); else { rh0 = __ldg(rh); rh1 = __ldg(rh + 1); }
             if (SPLIT && p.res_lo) {
               const uint4 *rl = reinterpret_cast<const uint4 *>(p.res_lo + ro);
-              rl0 = __ldg(rl); rl1 = __ldg(rl + 1);
+              if (p.vec32) ldg256(rl, rl0, rl1); else { rl0 = __ldg(rl); rl1 = __ldg(rl + 1); }
             }
           }
           uint32_t v0[16], v1[16];
@@ -619,11 +729,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           tmem_ld_wait();
           if (!ok) continue;
           float r[16];
+          {
+            const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + co);   // co % 16 == 0: 64-byte aligned
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 bq = __ldg(b4 + q4);
+              r[4 * q4] = bq.x; r[4 * q4 + 1] = bq.y; r[4 * q4 + 2] = bq.z; r[4 * q4 + 3] = bq.w;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float x = __uint_as_float(v0[j]);
             if (SPLIT) x += __uint_as_float(v1[j]) * kLoInv;
-            r[j] = x + __ldg(p.bias + co + j);
+            r[j] += x;
           }
           if (has_res) {
             const __half *hh0 = reinterpret_cast<const __half *>(&rh0), *hh1 = reinterpret_cast<const __half *>(&rh1);
@@ -638,24 +756,29 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 16; ++j) split_store(p.relu ? fmaxf(r[j], 0.f) : r[j], hi[j], lo[j]);
           const size_t oo = pix * p.out_ctot + p.out_coff + co;
+          const uint4 *hv = reinterpret_cast<const uint4 *>(hi), *lv = reinterpret_cast<const uint4 *>(lo);
           uint4 *oh4 = reinterpret_cast<uint4 *>(p.out_hi + oo);
-          oh4[0] = reinterpret_cast<const uint4 *>(hi)[0];
-          oh4[1] = reinterpret_cast<const uint4 *>(hi)[1];
+          if (p.vec32) stg256(oh4, hv[0], hv[1]); else { oh4[0] = hv[0]; oh4[1] = hv[1]; }
           if (SPLIT && p.out_lo) {
             uint4 *ol4 = reinterpret_cast<uint4 *>(p.out_lo + oo);
-            ol4[0] = reinterpret_cast<const uint4 *>(lo)[0];
-            ol4[1] = reinterpret_cast<const uint4 *>(lo)[1];
+            if (p.vec32) stg256(ol4, lv[0], lv[1]); else { ol4[0] = lv[0]; ol4[1] = lv[1]; }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty0 + 8u * buf) : "memory");
-      if (p.dbg && threadIdx.x == 32 * (kHaloProd + 1)) { long long e2 = clock64(); atomicAdd(p.dbg + blockIdx.x * 16 + 5, (unsigned long long)(e1 - e0)); atomicAdd(p.dbg + blockIdx.x * 16 + 6, (unsigned long long)(e2 - e1)); atomicAdd(p.dbg + blockIdx.x * 16 + 7, 1ull); }
+      if (p.dbg && threadIdx.x == 32 * (kHaloProd + kHaloIssue)) { long long e2 = clock64(); atomicAdd(p.dbg + blockIdx.x * 16 + 5, (unsigned long long)(e1 - e0)); atomicAdd(p.dbg + blockIdx.x * 16 + 6, (unsigned long long)(e2 - e1)); atomicAdd(p.dbg + blockIdx.x * 16 + 7, 1ull); }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long g_exit;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_exit));
+    p.dbg[blockIdx.x * 16 + 10] = g_exit;
+    p.dbg[blockIdx.x * 16 + 11] = (unsigned long long)(clock64() - c_entry);     // cycles in the kernel
+  }
   if (warp == kHaloProd) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -724,6 +847,14 @@ static bool encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t 
 }
 
 
+// 256-bit epilogue accesses need every row of the output (and residual) slice to start on a 32-byte boundary
+static int rows_vec32(const ActView &out, const ActView *res) {
+  auto ok = [](const ActView &v) {
+    return v.Ctot % 16 == 0 && v.coff % 16 == 0 && ((uintptr_t)v.hi & 31) == 0 && (!v.lo || ((uintptr_t)v.lo & 31) == 0);
+  };
+  return ok(out) && (!res || ok(*res)) ? 1 : 0;
+}
+
 static bool halo_enabled() {
   static int v = -1;
   if (v < 0) { const char *e = getenv("SHAPY_CONV_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -762,15 +893,16 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
       const int last = ((TN - 1) * Hb + (R - 1)) * Wp + W;   // positions that produce valid outputs
       const int MT = ceil_div(last, 128);
       if (MT > mt_max) return;
-      const size_t PS = align_up((size_t)std::max(P, MT * 128 + 2 * Wp + 2) * 16, 128);
-      const size_t slice = align_up((size_t)(kch / 8) * parts * PS, 1024);
+      const size_t slice = parts * align_up((size_t)std::max(P, MT * 128 + 2 * Wp + 2) * kch * 2, 1024);
       if (2 * slice + (bres ? b_all : 2 * b_blk) > 216 * 1024) return;
       const int n_super = ceil_div(N, TN) * bands;
       const double items = (double)n_super * n_tiles;
       const double a_bytes = (double)P * w.cin * 2 * parts * 2.0;                  // x2: 16-byte rows use half a sector
       const double b_bytes = bres ? 0.0 : 9.0 * NT * w.cin * 2 * parts;
       const double mem = (a_bytes + b_bytes) / l2_bpc;
-      // MMA time is bound by the shared-memory operand reads (~85 B/cycle measured): 4 KB of A + the B rows
+      // MMA time per k-step.  tools/umma_bench.cu measures max(32 + N/4, N/2) cycles (operand reads at 128 B/cycle or
+      // the tensor pipe); inside the kernel the issuing warps add ~30 %, which the 85 B/cycle figure below stands for
+      // (the tile configurations it selects were validated layer by layer, see profiles/README.md).
       auto mma_cyc = [](double n) { return std::max((4096.0 + 32.0 * n) / 85.0, n * 0.5); };
       const double per_k16 = split ? mma_cyc(2.0 * NT) + mma_cyc(NT) : mma_cyc(NT);
       const double mma = MT * 9.0 * (w.cin / 16) * per_k16;
@@ -801,9 +933,20 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   p.n_super = best.n_super; p.MT = best.MT;
   p.cin = w.cin; p.cout = w.cout; p.NT = best.NT; p.n_tiles = w.cout / best.NT; p.ncg = w.cin / kch;
   p.acc_bufs = (best.MT * best.NT * parts <= 256) ? 2 : 1;
+  p.n_iss = best.MT >= 2 ? kHaloIssue : 1;
+  {
+    const char *e = getenv("SHAPY_CONV_ROWSCHED");
+    p.row_sched = (best.TN == 1 && p.n_tiles == 1 && best.R < H && e && e[0] == '1') ? 1 : 0;   // off by default: no gain measured
+  }
+  if (const char *e = getenv("SHAPY_CONV_ISS")) p.n_iss = std::max(1, std::min(p.n_iss, atoi(e)));   // experiments
   const int P = best.TN * best.Hb * Wp;
-  p.PS = (uint32_t)align_up((size_t)std::max(P, best.MT * 128 + 2 * Wp + 2) * 16, 128);
-  p.a_slice_bytes = (uint32_t)align_up((size_t)(kch / 8) * parts * p.PS, 1024);
+  {
+    const char *b = getenv("SHAPY_CONV_BASEOFF");
+    p.a_baseoff = (b && b[0] == '1') ? 1 : 0;   // measured: the swizzle is a function of the absolute address, no base offset needed
+  }
+  // [position][kch] rows; rows past the box (read by the last m-tile's shifted taps) are never written
+  p.part_bytes = (uint32_t)align_up((size_t)std::max(P, best.MT * 128 + 2 * Wp + 2) * kch * 2, 1024);
+  p.a_slice_bytes = p.part_bytes * parts;
   p.a_tx = (uint32_t)((size_t)(kch / 8) * parts * P * 16);
   p.b_bytes = (uint32_t)best.NT * kch * 2;
   p.b_stride = (uint32_t)align_up((size_t)p.b_bytes * parts, 1024);
@@ -819,28 +962,28 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   p.idesc = (1u << 4) | ((uint32_t)(best.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.idesc2 = (1u << 4) | ((uint32_t)((2 * best.NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.relu = relu;
+  p.vec32 = rows_vec32(out, res);
   p.bias = w.bias;
   p.out_hi = out.hi; p.out_lo = out.lo; p.out_ctot = out.Ctot; p.out_coff = out.coff;
   p.res_hi = res ? res->hi : nullptr; p.res_lo = res ? res->lo : nullptr;
   p.res_ctot = res ? res->Ctot : 0; p.res_coff = res ? res->coff : 0;
-  p.in_hi = in.hi; p.in_lo = in.lo; p.in_ctot = in.Ctot; p.in_coff = in.coff;
   p.dbg = nullptr;
   pl->smem = 2 * (size_t)p.a_slice_bytes + b_stage * p.bstages + 16 * p.bstages + 128 + 1024;
   if (getenv("SHAPY_CONV_DEBUG"))
-    fprintf(stderr, "[halo] cin %d cout %d %dx%d N %d kch %d: NT %d TN %d R %d MT %d bands %d items %d PS %u slice %u bstages %d acc_bufs %d bres %d smem %zu\n",
-            w.cin, w.cout, H, W, N, kch, p.NT, p.TN, p.R, p.MT, p.bands, p.n_super * p.n_tiles, p.PS,
+    fprintf(stderr, "[halo] cin %d cout %d %dx%d N %d kch %d: NT %d TN %d R %d MT %d bands %d items %d part %u slice %u bstages %d acc_bufs %d bres %d smem %zu\n",
+            w.cin, w.cout, H, W, N, kch, p.NT, p.TN, p.R, p.MT, p.bands, p.n_super * p.n_tiles, p.part_bytes,
             p.a_slice_bytes, p.bstages, p.acc_bufs, p.b_resident, pl->smem);
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->grid = dim3(std::min(p.n_super * p.n_tiles, sms), 1);
+    pl->grid = dim3(std::min(p.row_sched ? N * H : p.n_super * p.n_tiles, sms), 1);
   }
   cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
   cuuint64_t strides[3] = {(cuuint64_t)in.Ctot * 2, (cuuint64_t)in.W * in.Ctot * 2, (cuuint64_t)in.H * in.W * in.Ctot * 2};
-  cuuint32_t box[4] = {8, (cuuint32_t)Wp, (cuuint32_t)best.Hb, (cuuint32_t)best.TN};
-  bool ok = encode(&p.a_hi, in.hi + in.coff, 4, dims, strides, box, 8);
-  if (split) ok = ok && encode(&p.a_lo, in.lo + in.coff, 4, dims, strides, box, 8);
+  cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)Wp, (cuuint32_t)best.Hb, (cuuint32_t)best.TN};
+  bool ok = encode(&p.a_hi, in.hi + in.coff, 4, dims, strides, box, kch);
+  if (split) ok = ok && encode(&p.a_lo, in.lo + in.coff, 4, dims, strides, box, kch);
   cuuint64_t bd[3] = {(cuuint64_t)w.cin, (cuuint64_t)w.cout, 9};
   cuuint64_t bs[2] = {(cuuint64_t)w.cin * 2, (cuuint64_t)w.cin * w.cout * 2};
   cuuint32_t bb[3] = {(cuuint32_t)kch, (cuuint32_t)best.NT, 1};
@@ -874,7 +1017,7 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
   {
     // cout tile: balance SM utilisation (tiles per 148 CTAs) against the per-MMA operand-read cost (see halo model)
     const double m_tiles = (double)p.tiles_w * p.tiles_h * p.tiles_n;
-    auto mma_cyc = [](double n) { return std::max((4096.0 + 32.0 * n) / 85.0, n * 0.5); };
+    auto mma_cyc = [](double n) { return std::max((4096.0 + 32.0 * n) / 128.0, n * 0.5); };
     double best = 1e30;
     int best_nt = pick_nt(w.cout);
     for (int nt = 128; nt >= 16; nt -= 16) {
@@ -884,9 +1027,11 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
       if (cost < best) { best = cost; best_nt = nt; }
     }
     p.NT = best_nt;
+    if (const char *e = getenv("SHAPY_CONV_NT")) { const int v = atoi(e); if (v >= 16 && v <= 128 && w.cout % v == 0) p.NT = v; }   // experiments
   }
   p.kpt = w.cin / kch;
   p.relu = relu;
+  p.vec32 = rows_vec32(out, res);
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B, N>>3 at 17, M>>4 at 24
   p.idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   uint32_t cols = p.NT * (split ? 2 : 1), pow2 = 32;
@@ -904,6 +1049,9 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
     if (p.kpt % g == 0 && (size_t)g * kblk <= 49152) { G = g; break; }
   p.G = G;
   const size_t stage = (size_t)G * kblk;
+  if (getenv("SHAPY_CONV_DEBUG"))
+    fprintf(stderr, "[per-tap] cin %d cout %d k %d s %d %dx%d N %d kch %d: NT %d tile %dx%dx%d tiles %d G %d\n", w.cin, w.cout, w.ksize,
+            w.stride, out.H, out.W, out.N, kch, p.NT, p.TW, p.TH, p.TN, p.tiles_w * p.tiles_h * p.tiles_n * (w.cout / p.NT), G);
   const int iters = p.ksize * p.ksize * p.kpt / G;
   // one persistent CTA per SM owns (almost) all of its shared memory
   int stages = (int)std::min<size_t>(8, (200 * 1024) / stage);
@@ -1006,6 +1154,7 @@ static int launch_halo_t(const UmmaPlan *pl, cudaStream_t st) {
     cudaMalloc(&d, 148 * 16 * 8);
     cudaMemset(d, 0, 148 * 16 * 8);
     hp.dbg = d;
+    if (const char *f = getenv("SHAPY_CONV_DBGFLAGS")) hp.dbg_flags = atoi(f);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
@@ -1021,6 +1170,15 @@ static int launch_halo_t(const UmmaPlan *pl, cudaStream_t st) {
     const double n = pl->grid.x;
     fprintf(stderr, "[phases] cin %d cout %d %dx%d MT %d NT %d: %.1f us | per CTA cycles: prod wait_empty %.0f fill %.0f | mma wait_acc %.0f wait_a %.0f busy_total %.0f | epi wait_full %.0f work %.0f items %.1f\n",
             hp.cin, hp.cout, hp.H, hp.W, hp.MT, hp.NT, ms * 1e3, sum[0] / n, sum[1] / n, sum[2] / n, sum[3] / n, sum[4] / n, sum[5] / n, sum[6] / n, sum[7] / n);
+    {
+      unsigned long long g0 = ~0ull, g0max = 0, g1 = 0, pro = 0, cyc = 0;
+      for (int c = 0; c < (int)pl->grid.x; ++c) {
+        g0 = std::min(g0, h[c * 16 + 9]); g0max = std::max(g0max, h[c * 16 + 9]); g1 = std::max(g1, h[c * 16 + 10]);
+        pro += h[c * 16 + 8]; cyc = std::max(cyc, h[c * 16 + 11]);
+      }
+      fprintf(stderr, "[phases]   first entry -> last exit %.1f us, entry skew %.1f us, prologue %.0f cycles avg, longest CTA %llu cycles (%.2f GHz)\n",
+              (g1 - g0) * 1e-3, (g0max - g0) * 1e-3, pro / n, cyc, cyc / ((g1 - g0) * 1.0));
+    }
     cudaFree(d);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     shapy::count_launch();

@@ -271,6 +271,23 @@ extern "C" int shapy_conv_test(const shapy_conv_desc_t *conv, const float *x, co
     plan = umma_plan_create(w, in, out, res ? &rv : nullptr, relu != 0);
     if (!plan) { cleanup(); return SHAPY_ERR_UNSUPPORTED; }
     rc = umma_plan_launch(plan, st);
+    if (const char *reps_s = getenv("SHAPY_CONV_TEST_REPS")) {
+      // timing aid for kernel work: re-launch the same plan and report the average launch time
+      const int reps = atoi(reps_s);
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+      for (int i = 0; i < reps && !rc; ++i) rc = umma_plan_launch(plan, st);
+      cudaEventRecord(e1, st);
+      cudaStreamSynchronize(st);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double fl = 2.0 * B * Ho * Wo * (double)conv->cout * conv->cin * conv->ksize * conv->ksize;
+      fprintf(stderr, "[conv_test] cin %d cout %d k %d s %d %dx%d B %d mode %d: %.2f us/launch, %.1f TFLOP/s (x%d MMA flops)\n",
+              conv->cin, conv->cout, conv->ksize, conv->stride, H, W, B, mode, ms * 1e3 / reps, fl / (ms * 1e-3 / reps) * 1e-12,
+              mode ? 3 : 1);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
   } else {
     rc = launch_conv_simt(w, in, out, res ? &rv : nullptr, relu != 0, st);
   }
