@@ -535,13 +535,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     } else if (warp == 1) {
       if (elect_one()) {
         if (p.b_resident) {
-          mbar_expect_tx(b_full(0), p.b_bytes * PARTS * 9u * p.ncg);
-          for (int cg = 0; cg < p.ncg; ++cg)
+          // all 9 x ncg weight blocks of the (single) cout tile stay in shared memory for the whole kernel; one barrier
+          // per channel group, so the first MMAs start after a third of the weights has landed
+          for (int cg = 0; cg < p.ncg; ++cg) {
+            mbar_expect_tx(b_full(cg), p.b_bytes * PARTS * 9u);
             for (int tap = 0; tap < 9; ++tap) {
               const uint32_t bb = b_base + b_stage_bytes * (cg * 9 + tap);
-              tma_load_3d(bb, &p.b_hi, b_full(0), cg * KCH, 0, tap);
-              if (SPLIT) tma_load_3d(bb + p.b_bytes, &p.b_lo, b_full(0), cg * KCH, 0, tap);
+              tma_load_3d(bb, &p.b_hi, b_full(cg), cg * KCH, 0, tap);
+              if (SPLIT) tma_load_3d(bb + p.b_bytes, &p.b_lo, b_full(cg), cg * KCH, 0, tap);
             }
+          }
         } else {
           int bs = 0;
           uint32_t bph = 0;
@@ -571,7 +574,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (iw < p.n_iss) {
       int bs = 0, slice = 0, lt = 0;
       uint32_t bph = 0, aph = 0;
-      if (p.b_resident) mbar_wait(b_full(0), 0);
       // Descriptor low words are advanced with 32-bit adds only; everything else is hoisted here.  (Measured with
       // SHAPY_CONV_DBGFLAGS=7: the previous per-tap 64-bit descriptor set-up cost ~250 cycles per tap and made the
       // whole kernel issue-bound.)
@@ -661,6 +663,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const uint32_t dbase = tmem_base + buf * 256u + m_d;
         for (int cg = 0; cg < ncg; ++cg) {
           long long m2 = clock64();
+          if (p.b_resident && lt == 0) mbar_wait(b_full(cg), 0);   // resident weights of this channel group have landed
           mbar_wait(a_full0 + 8u * slice, aph);
           if (rec) atomicAdd(p.dbg + blockIdx.x * 16 + 3, (unsigned long long)(clock64() - m2));
           tc_fence_after();
@@ -1001,13 +1004,23 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
   memset(&pl->p, 0, sizeof(pl->p));
   UmmaParams &p = pl->p;
   const bool split = in.lo != nullptr;
-  const int kch = pick_kch(w.cin);
-  pl->kch = kch;
-  pl->split = split;
+  int kch = pick_kch(w.cin);
   if (w.ksize == 3 && w.stride == 1 && halo_enabled() && kch <= halo_max_kch() && halo_configure(pl, w, in, out, res, relu)) {
+    pl->kch = kch;
+    pl->split = split;
     pl->halo = true;
     return pl;
   }
+  // K padding: channel counts that are not a multiple of 64 still use 64-channel (128-byte, SWIZZLE_128B) k-blocks; the
+  // TMA unit zero-fills the channels past cin of both operands.  These layers are bound by TMA requests and barrier
+  // round trips, not by the tensor pipe: one k-block per tap instead of three was 10-18 % faster on every cin = 48 / 96
+  // layer (SHAPY_CONV_KPAD=0 restores exact-width k-blocks).
+  {
+    const char *e = getenv("SHAPY_CONV_KPAD");
+    if (!(e && e[0] == '0') && kch < 64) kch = 64;
+  }
+  pl->kch = kch;
+  pl->split = split;
   p.N = out.N; p.Ho = out.H; p.Wo = out.W;
   p.TW = std::min(out.W, 128);
   p.TH = std::max(1, std::min(out.H, 128 / p.TW));
@@ -1029,7 +1042,7 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
     p.NT = best_nt;
     if (const char *e = getenv("SHAPY_CONV_NT")) { const int v = atoi(e); if (v >= 16 && v <= 128 && w.cout % v == 0) p.NT = v; }   // experiments
   }
-  p.kpt = w.cin / kch;
+  p.kpt = ceil_div(w.cin, kch);
   p.relu = relu;
   p.vec32 = rows_vec32(out, res);
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B, N>>3 at 17, M>>4 at 24

@@ -14,6 +14,7 @@ LAYERS = {  # name: (cin, cout, k, stride, H)
     'c48': (48, 48, 3, 1, 56), 'c96': (96, 96, 3, 1, 28), 'c192': (192, 192, 3, 1, 14), 'c384': (384, 384, 3, 1, 7),
     'b64': (64, 64, 3, 1, 56), 'b1x1a': (256, 64, 1, 1, 56), 'b1x1b': (64, 256, 1, 1, 56),
     't48': (256, 48, 3, 1, 56), 'd96': (48, 96, 3, 2, 56), 'f1x1': (96, 48, 1, 1, 28),
+    'd48': (48, 48, 3, 2, 56), 'd192': (48, 192, 3, 2, 28), 's2_96_192': (96, 192, 3, 2, 28),
 }
 g = torch.Generator().manual_seed(0)
 for name, (cin, cout, k, s, H) in LAYERS.items():

@@ -14,7 +14,7 @@ df = df[df['Metric Name'] == 'gpu__time_duration.sum']
 df['us'] = df['Metric Value'].astype(str).str.replace(',', '').astype(float) / 1000
 names = df['Kernel Name'].astype(str).tolist()
 us = df['us'].tolist()
-keep = [(n, t) for n, t in zip(names, us) if any(s in n for s in ('conv_', 'stem_kernel', 'fuse_kernel', 'pool_kernel'))]
+keep = [(n, t) for n, t in zip(names, us) if any(s in n for s in ('conv_', 'stem', 'fuse_kernel', 'pool_kernel'))]
 model = synth.build_synthetic_regressor()
 convs, ops, slots, feat, layer_slots = model.backbone.build_program()
 assert len(keep) == len(ops), (len(keep), len(ops))
