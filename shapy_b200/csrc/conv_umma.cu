@@ -396,11 +396,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 // (and discarded by the epilogue); in exchange activations cross L2 ~1.2-1.5x instead of 9x, and the
 // weights of one (tap, channel group) are shared by up to 5 m-tiles held in TMEM at once.
 struct alignas(64) HaloParams {
-  CUtensorMap a_hi, a_lo;  // (8ch, W, H, N) unswizzled, box (8, Wp, Hb, TN)
+  CUtensorMap a_hi[4], a_lo[4];  // stride 1: [0] = (C, W, H, N); stride 2: the four parity views [row parity * 2 + column
+                                 // parity] of the input, each (C, W/2, H/2, N); box (KCH, Wp, Hb, TN), swizzled rows
   CUtensorMap b_hi, b_lo;  // (cin, cout, 9) swizzled, box (KCH, NT, 1)
   int N, H, W;
   int Wp, Hb, TN, R, bands, n_super, MT;
   int cin, cout, NT, n_tiles, ncg, bstages, acc_bufs, b_resident, n_iss;
+  int stride;       // 1 or 2 (3x3 both); for stride 2, N / H / W are the OUTPUT extent and the A slice holds 4 parity planes
+  uint32_t plane_bytes;  // size of one plane of an A slice part (stride 1: == part_bytes)
   int row_sched;    // 1: each CTA owns a contiguous range of the N*H output rows, walked in chunks of <= R rows
   int a_baseoff;    // 1: put (start >> 7) & 7 into the descriptor's base-offset field for row-shifted starts
   uint32_t part_bytes;   // offset of the lo part inside an A slice
@@ -523,8 +526,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
             } else {
               mbar_expect_tx(fb, p.a_tx);
-              tma_load_4d(sb, &p.a_hi, fb, cg * KCH, -1, h0 - 1, n0);
-              if (SPLIT) tma_load_4d(sb + p.part_bytes, &p.a_lo, fb, cg * KCH, -1, h0 - 1, n0);
+              if (p.stride == 1) {
+                tma_load_4d(sb, &p.a_hi[0], fb, cg * KCH, -1, h0 - 1, n0);
+                if (SPLIT) tma_load_4d(sb + p.part_bytes, &p.a_lo[0], fb, cg * KCH, -1, h0 - 1, n0);
+              } else {
+                // plane (py, px) holds input rows 2y + py, columns 2x + px: the odd planes start one row / column early
+                // (row -1 / column -1 are out of range = the zero padding)
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) {
+                  const int x0 = (pl & 1) ? -1 : 0, y0 = h0 + ((pl >> 1) ? -1 : 0);
+                  tma_load_4d(sb + pl * p.plane_bytes, &p.a_hi[pl], fb, cg * KCH, x0, y0, n0);
+                  if (SPLIT) tma_load_4d(sb + p.part_bytes + pl * p.plane_bytes, &p.a_lo[pl], fb, cg * KCH, x0, y0, n0);
+                }
+              }
             }
             if (p.dbg) { long long t2 = clock64(); atomicAdd(p.dbg + blockIdx.x * 16 + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.dbg + blockIdx.x * 16 + 1, (unsigned long long)(t2 - t1)); }
             if (++slice == 2) { slice = 0; aph ^= 1; }
@@ -622,7 +636,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       };
       // all 9 taps of one channel group (the elected lane only)
       // per tap: start shift in descriptor units, and the high word (base offset = 128-byte line of the start, mod 8)
-      auto tap_shift = [&](int tap) { return ((uint32_t)(tap / 3) * wp + (uint32_t)(tap % 3)) * row_u; };
+      // stride 1: tap (ky, kx) reads position o + ky Wp + kx.  stride 2: input (2 oy + ky - 1, 2 ox + kx - 1) lives in
+      // parity plane (ky != 1, kx != 1) at position o (+ Wp for ky == 2) (+ 1 for kx == 2)
+      const uint32_t plane16 = p.plane_bytes >> 4;
+      const bool s2 = p.stride == 2;
+      auto tap_shift = [&](int tap) {
+        const uint32_t ky = (uint32_t)(tap / 3), kx = (uint32_t)(tap % 3);
+        return s2 ? ((ky != 1) * 2u + (kx != 1)) * plane16 + ((ky == 2) * wp + (kx == 2)) * row_u : (ky * wp + kx) * row_u;
+      };
       auto tap_hi = [&](int tap) {
         const uint32_t line = (tap_shift(tap) << 4) >> 7;
         return baseoff ? (a_hi32 | ((line & 7u) << 17)) : a_hi32;
@@ -871,13 +892,25 @@ static int halo_max_kch() {
   return v;
 }
 
+// stride-2 layers: 0 disables the halo variant for them (SHAPY_CONV_HALO_S2_MAXKCH)
+static int halo_s2_max_kch() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SHAPY_CONV_HALO_S2_MAXKCH"); v = e ? atoi(e) : 32; }
+  return v;
+}
+
 // Chooses the super-tile of the halo-resident kernel by a small traffic / MMA cost model.
 static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, const ActView &out, const ActView *res,
                            bool relu) {
   const bool split = in.lo != nullptr;
   const int parts = split ? 2 : 1;
   const int kch = pick_kch(w.cin);
-  const int H = out.H, W = out.W, N = out.N, Wp = W + 2;
+  // stride 1: one plane of the input band with a 1-pixel halo.  stride 2: four parity planes (row parity x column parity)
+  // of output size + 1; H, W are the OUTPUT extent in both cases.
+  const int stride = w.stride;
+  const int H = out.H, W = out.W, N = out.N;
+  const int Wp = stride == 1 ? W + 2 : W + 1, hpad = stride == 1 ? 2 : 1, nplanes = stride == 1 ? 1 : 4;
+  const int maxshift = stride == 1 ? 2 * Wp + 2 : Wp + 1;
   if (Wp > 256) return false;
   struct Cfg { int NT, TN, R, MT, Hb, bands, n_super, bres; double cost; } best = {0, 0, 0, 0, 0, 0, 0, 0, 1e30};
   const double sm_count = 148.0, l2_bpc = 19.6;   // measured ~5.5 TB/s of L2->SM traffic = 19.6 B/cycle/SM
@@ -890,17 +923,17 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     const size_t b_all = b_blk * 9 * (w.cin / kch);
     const bool bres = n_tiles == 1 && b_all <= 120 * 1024;
     auto consider = [&](int TN, int R) {
-      const int Hb = R + 2;
+      const int Hb = R + hpad;
       const int bands = ceil_div(H, R);
       const int P = TN * Hb * Wp;
       const int last = ((TN - 1) * Hb + (R - 1)) * Wp + W;   // positions that produce valid outputs
       const int MT = ceil_div(last, 128);
       if (MT > mt_max) return;
-      const size_t slice = parts * align_up((size_t)std::max(P, MT * 128 + 2 * Wp + 2) * kch * 2, 1024);
+      const size_t slice = (size_t)parts * nplanes * align_up((size_t)std::max(P, MT * 128 + maxshift) * kch * 2, 1024);
       if (2 * slice + (bres ? b_all : 2 * b_blk) > 216 * 1024) return;
       const int n_super = ceil_div(N, TN) * bands;
       const double items = (double)n_super * n_tiles;
-      const double a_bytes = (double)P * w.cin * 2 * parts * 2.0;                  // x2: 16-byte rows use half a sector
+      const double a_bytes = (double)nplanes * P * w.cin * 2 * parts;
       const double b_bytes = bres ? 0.0 : 9.0 * NT * w.cin * 2 * parts;
       const double mem = (a_bytes + b_bytes) / l2_bpc;
       // MMA time per k-step.  tools/umma_bench.cu measures max(32 + N/4, N/2) cycles (operand reads at 128 B/cycle or
@@ -917,7 +950,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     for (int TN = 1; TN <= std::min(N, 8); ++TN) consider(TN, H);   // whole images
     for (int R = 1; R < H; ++R) consider(1, R);                     // bands of one image
   }
-  if (best.NT) {
+  if (best.NT && stride == 1) {
     // per-tap kernel estimate: every (m-tile, n-tile) streams 9 taps of A and B through L2
     const int TWt = std::min(W, 128), THt = std::max(1, std::min(H, 128 / TWt));
     const int TNt = (TWt == W && THt == H) ? std::max(1, std::min(N, 128 / (TWt * THt))) : 1;
@@ -932,6 +965,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   if (!best.NT) return false;
   HaloParams &p = pl->hp;
   memset(&p, 0, sizeof(p));
+  p.stride = stride;
   p.N = N; p.H = H; p.W = W; p.Wp = Wp; p.Hb = best.Hb; p.TN = best.TN; p.R = best.R; p.bands = best.bands;
   p.n_super = best.n_super; p.MT = best.MT;
   p.cin = w.cin; p.cout = w.cout; p.NT = best.NT; p.n_tiles = w.cout / best.NT; p.ncg = w.cin / kch;
@@ -939,7 +973,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   p.n_iss = best.MT >= 2 ? kHaloIssue : 1;
   {
     const char *e = getenv("SHAPY_CONV_ROWSCHED");
-    p.row_sched = (best.TN == 1 && p.n_tiles == 1 && best.R < H && e && e[0] == '1') ? 1 : 0;   // off by default: no gain measured
+    p.row_sched = (stride == 1 && best.TN == 1 && p.n_tiles == 1 && best.R < H && e && e[0] == '1') ? 1 : 0;   // off by default: no gain measured
   }
   if (const char *e = getenv("SHAPY_CONV_ISS")) p.n_iss = std::max(1, std::min(p.n_iss, atoi(e)));   // experiments
   const int P = best.TN * best.Hb * Wp;
@@ -948,9 +982,10 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     p.a_baseoff = (b && b[0] == '1') ? 1 : 0;   // measured: the swizzle is a function of the absolute address, no base offset needed
   }
   // [position][kch] rows; rows past the box (read by the last m-tile's shifted taps) are never written
-  p.part_bytes = (uint32_t)align_up((size_t)std::max(P, best.MT * 128 + 2 * Wp + 2) * kch * 2, 1024);
+  p.plane_bytes = (uint32_t)align_up((size_t)std::max(P, best.MT * 128 + maxshift) * kch * 2, 1024);
+  p.part_bytes = p.plane_bytes * nplanes;
   p.a_slice_bytes = p.part_bytes * parts;
-  p.a_tx = (uint32_t)((size_t)(kch / 8) * parts * P * 16);
+  p.a_tx = (uint32_t)((size_t)parts * nplanes * P * kch * 2);
   p.b_bytes = (uint32_t)best.NT * kch * 2;
   p.b_stride = (uint32_t)align_up((size_t)p.b_bytes * parts, 1024);
   const size_t b_stage = (size_t)p.b_stride;
@@ -982,11 +1017,26 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     pl->grid = dim3(std::min(p.row_sched ? N * H : p.n_super * p.n_tiles, sms), 1);
   }
-  cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
-  cuuint64_t strides[3] = {(cuuint64_t)in.Ctot * 2, (cuuint64_t)in.W * in.Ctot * 2, (cuuint64_t)in.H * in.W * in.Ctot * 2};
   cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)Wp, (cuuint32_t)best.Hb, (cuuint32_t)best.TN};
-  bool ok = encode(&p.a_hi, in.hi + in.coff, 4, dims, strides, box, kch);
-  if (split) ok = ok && encode(&p.a_lo, in.lo + in.coff, 4, dims, strides, box, kch);
+  bool ok = true;
+  for (int pl_i = 0; pl_i < nplanes && ok; ++pl_i) {
+    cuuint64_t dims[4], strides[3];
+    size_t off;
+    if (stride == 1) {
+      dims[0] = in.C; dims[1] = in.W; dims[2] = in.H; dims[3] = in.N;
+      strides[0] = (cuuint64_t)in.Ctot * 2; strides[1] = (cuuint64_t)in.W * in.Ctot * 2;
+      strides[2] = (cuuint64_t)in.H * in.W * in.Ctot * 2;
+      off = in.coff;
+    } else {   // parity view: rows 2y + py, columns 2x + px of the input
+      const int py = pl_i >> 1, px = pl_i & 1;
+      dims[0] = in.C; dims[1] = in.W / 2; dims[2] = in.H / 2; dims[3] = in.N;
+      strides[0] = (cuuint64_t)in.Ctot * 4; strides[1] = (cuuint64_t)in.W * in.Ctot * 4;
+      strides[2] = (cuuint64_t)in.H * in.W * in.Ctot * 2;
+      off = (size_t)in.coff + ((size_t)py * in.W + px) * in.Ctot;
+    }
+    ok = ok && encode(&p.a_hi[pl_i], in.hi + off, 4, dims, strides, box, kch);
+    if (split) ok = ok && encode(&p.a_lo[pl_i], in.lo + off, 4, dims, strides, box, kch);
+  }
   cuuint64_t bd[3] = {(cuuint64_t)w.cin, (cuuint64_t)w.cout, 9};
   cuuint64_t bs[2] = {(cuuint64_t)w.cin * 2, (cuuint64_t)w.cin * w.cout * 2};
   cuuint32_t bb[3] = {(cuuint32_t)kch, (cuuint32_t)best.NT, 1};
@@ -1005,7 +1055,8 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
   UmmaParams &p = pl->p;
   const bool split = in.lo != nullptr;
   int kch = pick_kch(w.cin);
-  if (w.ksize == 3 && w.stride == 1 && halo_enabled() && kch <= halo_max_kch() && halo_configure(pl, w, in, out, res, relu)) {
+  if (w.ksize == 3 && halo_enabled() && kch <= (w.stride == 1 ? halo_max_kch() : halo_s2_max_kch()) &&
+      halo_configure(pl, w, in, out, res, relu)) {
     pl->kch = kch;
     pl->split = split;
     pl->halo = true;

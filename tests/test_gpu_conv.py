@@ -22,6 +22,8 @@ SHAPES = [
     (1536, 512, 1, 1, 7, 7, 2),
     (512, 2048, 1, 1, 7, 7, 2),    # 16 n-tiles
     (48, 48, 3, 1, 8, 24, 1),      # non-square small map
+    (96, 192, 3, 2, 28, 28, 2),    # stride-2 halo variant, KCH=32, two cout tiles
+    (48, 48, 3, 2, 16, 24, 3),     # stride-2 halo variant, non-square, whole-image items
     (64, 64, 3, 1, 136, 136, 1),   # W > 128 is not tiled by the tcgen05 engine -> unsupported, see below
 ]
 

@@ -15,6 +15,7 @@ LAYERS = {  # name: (cin, cout, k, stride, H)
     'b64': (64, 64, 3, 1, 56), 'b1x1a': (256, 64, 1, 1, 56), 'b1x1b': (64, 256, 1, 1, 56),
     't48': (256, 48, 3, 1, 56), 'd96': (48, 96, 3, 2, 56), 'f1x1': (96, 48, 1, 1, 28),
     'd48': (48, 48, 3, 2, 56), 'd192': (48, 192, 3, 2, 28), 's2_96_192': (96, 192, 3, 2, 28),
+    's2_64': (64, 64, 3, 2, 112), 's2_192_384': (192, 384, 3, 2, 14), 's2_256_96': (256, 96, 3, 2, 56),
 }
 g = torch.Generator().manual_seed(0)
 for name, (cin, cout, k, s, H) in LAYERS.items():
