@@ -257,9 +257,32 @@ def main():
             for k in out_host:
                 out_host[k].copy_(res[k], non_blocking=True)
 
-    for _ in range(W):
-        step_e2e()
-    e2e_ms = timed(step_e2e, K) / K
+    if world == 1:
+        # one GPU: the public serving loop (shapy_b200.pipeline.HostPipeline) -- H2D of batch i+1 and D2H of batch i-1
+        # overlap the forward of batch i on separate streams.  All K batches (copies, forwards, the L2 flush before each
+        # forward) sit inside ONE timed interval.
+        from shapy_b200.pipeline import HostPipeline
+        outs2 = [out_host, {k: torch.empty_like(v).pin_memory() for k, v in out_host.items()}]
+
+        def run_e2e(k):
+            pipe = HostPipeline(model, dev)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(k):
+                pipe.submit(full_host, outs2[i % 2], between=flush.zero_)
+            pipe.drain()
+            b.record()
+            barrier()
+            return a.elapsed_time(b)
+        run_e2e(W)
+        e2e_ms = run_e2e(K) / K
+        e2e_mode = 'pipelined: H2D / forward / D2H on three streams, K batches in one timed interval (L2 flush included)'
+    else:
+        for _ in range(W):
+            step_e2e()
+        e2e_ms = timed(step_e2e, K) / K
+        e2e_mode = 'rank 0 holds the host buffers: H2D, NCCL scatter, forward, NCCL gather, D2H per step'
     e2e_value = world * B / (e2e_ms * 1e-3)
     h2d = world * per * 3 * 224 * 224 * 4
     d2h = world * per * (10475 * 3 + 10 + 5) * 4
@@ -326,7 +349,7 @@ def main():
                                    'measurements), 224x224, batch 64 per GPU', 'batch_per_gpu': B,
                        'l2': 'flushed (256 MB write) before every timed step', 'parallelism': f'dp{world}',
                        'precision_mode': args.mode},
-            'e2e': {'value': e2e_value, 'unit': 'bodies/s', 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
+            'e2e': {'value': e2e_value, 'unit': 'bodies/s', 'ms_per_step': e2e_ms, 'mode': e2e_mode, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
             'gpu_launches': int(launches_per_step * K),
             'clocks': clocks,

@@ -65,3 +65,25 @@ def test_full_regressor_vs_oracle():
     with torch.no_grad():
         out2 = m2(x.cuda())
     assert torch.equal(out2['stage_02']['vertices'], st['vertices'])
+
+
+def test_host_pipeline_matches_direct_calls():
+    """shapy_b200.pipeline.HostPipeline (overlapped H2D / forward / D2H) returns exactly what direct calls return."""
+    import torch
+    from shapy_b200 import synth
+    from shapy_b200.pipeline import HostPipeline, pack_result
+    model = synth.build_synthetic_regressor().cuda().eval()
+    g = torch.Generator().manual_seed(7)
+    xs = [torch.randn(3, 3, 224, 224, generator=g).pin_memory() for _ in range(4)]
+    outs = [dict(vertices=torch.empty(3, 10475, 3).pin_memory(), betas=torch.empty(3, 10).pin_memory(),
+                 measurements=torch.empty(3, 5).pin_memory()) for _ in range(4)]
+    pipe = HostPipeline(model, 'cuda')
+    for x, o in zip(xs, outs):
+        pipe.submit(x, o)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for x, o in zip(xs, outs):
+        with torch.no_grad():
+            ref = pack_result(model(x.cuda()))
+        for k in o:
+            assert torch.equal(o[k], ref[k].cpu()), k
