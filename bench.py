@@ -9,9 +9,10 @@ metric : bodies/sec, image -> SMPL-X vertices (+ betas, measurements), B = 64 pe
          "Full SHAPY_A regressor (HRNet + iterative head + fused SMPL-X), batch=64, 1xB200, fp32 tol 1e-4";
          configs[4] shards 64 images per GPU, i.e. weak scaling).
 value  : whole-job bodies/s with the images already resident in HBM (CUDA events, max over ranks).
-e2e    : the same metric through the reference-facing module call with HOST buffers: pinned host images ->
-         H2D -> (NCCL scatter) -> SMPLXRegressor.forward -> (NCCL gather) -> D2H of vertices / betas /
-         measurements, all inside the timed region.
+e2e    : the same metric through the public serving loop with HOST buffers (shapy_b200.pipeline.HostPipeline around
+         SMPLXRegressor.forward): every rank copies its own pinned host images H2D, runs the forward and copies
+         vertices / betas / measurements D2H, the three stages overlapped across consecutive batches on three
+         streams; all copies sit inside the timed region (one interval over the K batches, max over ranks).
 roofline: the dominant kernel is the tcgen05 implicit-GEMM convolution (HRNet = ~99 % of the step);
          achieved = algorithmic conv FLOPs (36.93 GFLOP / image @224^2) / HRNet device time.
          `roofline_lbs` / `roofline_shape` report the HBM rooflines of the fused SMPL-X kernels.
@@ -170,7 +171,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from shapy_b200 import _lib, dist as sdist, synth
+    from shapy_b200 import _lib, synth
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -238,51 +239,34 @@ def main():
     value = world * B / (ms_per_step * 1e-3)
 
     # ---------------------------------------------------------------- end-to-end with host buffers
+    # Every rank serves its own stream of batches from its own pinned host buffers through the public serving loop
+    # (shapy_b200.pipeline.HostPipeline): H2D of batch i+1 and D2H of batch i-1 overlap the forward of batch i on
+    # separate streams; the bodies are independent, so there is no data-path collective.  All K batches (copies,
+    # forwards, the L2 flush before each forward) sit inside ONE timed interval per rank; max over ranks.
+    from shapy_b200.pipeline import HostPipeline
     per = B
-    out_host = {'vertices': torch.empty(world * per, 10475, 3).pin_memory(), 'betas': torch.empty(world * per, 10).pin_memory(),
-                'measurements': torch.empty(world * per, 5).pin_memory()} if rank == 0 else None
-    full_host = torch.randn(world * per, 3, 224, 224, generator=g).pin_memory() if rank == 0 else None
+    full_host = torch.randn(per, 3, 224, 224, generator=g).pin_memory()
+    outs2 = [{'vertices': torch.empty(per, 10475, 3).pin_memory(), 'betas': torch.empty(per, 10).pin_memory(),
+              'measurements': torch.empty(per, 5).pin_memory()} for _ in range(2)]
 
-    def step_e2e():
-        full_dev = full_host.to(dev, non_blocking=True) if rank == 0 else None
+    def run_e2e(k):
+        pipe = HostPipeline(model, dev)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(k):
+            pipe.submit(full_host, outs2[i % 2], between=flush.zero_)
+        pipe.drain()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
-            res = sdist.sharded_forward(model, full_dev, per, device=dev)
-        else:
-            with torch.no_grad():
-                o = model(full_dev)
-            st = o['stage_02']
-            res = dict(vertices=st['vertices'], betas=st['betas'],
-                       measurements=torch.stack([o['measurements'][k] for k in ('mass', 'height', 'chest', 'waist', 'hips')], 1))
-        if rank == 0:
-            for k in out_host:
-                out_host[k].copy_(res[k], non_blocking=True)
-
-    if world == 1:
-        # one GPU: the public serving loop (shapy_b200.pipeline.HostPipeline) -- H2D of batch i+1 and D2H of batch i-1
-        # overlap the forward of batch i on separate streams.  All K batches (copies, forwards, the L2 flush before each
-        # forward) sit inside ONE timed interval.
-        from shapy_b200.pipeline import HostPipeline
-        outs2 = [out_host, {k: torch.empty_like(v).pin_memory() for k, v in out_host.items()}]
-
-        def run_e2e(k):
-            pipe = HostPipeline(model, dev)
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(k):
-                pipe.submit(full_host, outs2[i % 2], between=flush.zero_)
-            pipe.drain()
-            b.record()
-            barrier()
-            return a.elapsed_time(b)
-        run_e2e(W)
-        e2e_ms = run_e2e(K) / K
-        e2e_mode = 'pipelined: H2D / forward / D2H on three streams, K batches in one timed interval (L2 flush included)'
-    else:
-        for _ in range(W):
-            step_e2e()
-        e2e_ms = timed(step_e2e, K) / K
-        e2e_mode = 'rank 0 holds the host buffers: H2D, NCCL scatter, forward, NCCL gather, D2H per step'
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    run_e2e(W)
+    e2e_ms = run_e2e(K) / K
+    e2e_mode = ('pipelined per rank: H2D / forward / D2H on three streams, K batches in one timed interval (L2 flush '
+                'included), max over ranks')
     e2e_value = world * B / (e2e_ms * 1e-3)
     h2d = world * per * 3 * 224 * 224 * 4
     d2h = world * per * (10475 * 3 + 10 + 5) * 4

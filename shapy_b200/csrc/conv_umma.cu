@@ -2,22 +2,39 @@
 //
 //   D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * Wt[tap][cout][cin]
 //
-// GEMM view: M = 128 output pixels (a TW x TH x TN box of the NHWC output), N = cout tile (<= 128),
-// K = taps * cin, walked in k-blocks of KCH in {16, 32, 64} channels of one filter tap.
-//  * A operand: one 4-D TMA box per (tap, k-block) straight out of the NHWC activation plane, the box
-//    origin shifted by the tap; out-of-image rows/columns are ZERO-FILLED by the TMA unit, which is the
-//    convolution's padding -- no im2col buffer, no halo storage.  Stride-2 layers use four parity views
-//    (even/odd row x even/odd column) of the same plane so every tap is again a dense box.
-//  * B operand: 3-D TMA box of the pre-packed [tap][cout][cin] fp16 weights (BN scale folded in).
-//  * Both land in shared memory in the canonical K-major SWIZZLE_{32,64,128}B layout (swizzle = KCH*2 B
-//    rows) that the UMMA shared-memory descriptor names, so no thread ever touches operand data.
-//  * One elected thread issues tcgen05.mma (M=128, N=cout tile, K=16) into fp32 TMEM accumulators;
-//    split-fp16 parity mode issues hi*hi into D0 and hi*lo + lo*hi into D1 (out = D0 + D1 / 2048).
-//  * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-//    (tcgen05.ld -> +bias (+residual) -> ReLU -> split to fp16 hi/lo -> 16-byte global stores).
-//    smem ring of `stages` slots with full/empty mbarriers; tcgen05.commit releases slots and publishes
-//    the accumulator.  Several CTAs share an SM (<= ~100 KB smem, <= 256 TMEM columns each) so one
-//    CTA's epilogue overlaps another's main loop.
+// GEMM view: M = 128 output pixels, N = cout tile (<= 128), K = taps * cin walked in 16-channel k-steps.
+// Two kernels share the PTX helpers, the epilogue and the weight layout:
+//
+//  conv_umma_kernel ("per-tap"): 1x1 convs, 64-channel-block 3x3 convs, anything the halo variant declines.
+//   * A: one 4-D TMA box per (tap, k-block) straight out of the NHWC activation plane, the box origin shifted by
+//     the tap; out-of-image rows/columns are ZERO-FILLED by the TMA unit = the padding (no im2col, no halo
+//     storage).  Stride-2 layers use four parity views of the same plane so every tap is again a dense box.
+//     Channel counts that are not a multiple of 64 still use 64-channel boxes: TMA zero-fills the channels past cin.
+//   * B: 3-D TMA box of the pre-packed [tap][cout][cin] fp16 weights (BN scale folded in).
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = kEpiWarps epilogue warps; smem ring
+//     of `stages` slots with full/empty mbarriers; two TMEM accumulator buffers so tile t's epilogue overlaps
+//     tile t+1's main loop; persistent, one CTA per SM.
+//
+//  conv_halo_kernel ("halo-resident"): 3x3 stride-1 and stride-2 convs with <= 32-channel k-blocks (C = 48 / 96:
+//   45 % of the network's time).  See the comment above the kernel.
+//
+// Common: operands land in the canonical K-major SWIZZLE_{32,64,128}B layout the UMMA shared-memory descriptor names,
+// so no thread ever touches operand data; one elected lane issues tcgen05.mma (M=128, N=cout tile, K=16) into fp32
+// TMEM accumulators.  Split-fp16 parity mode keeps activations and weights as fp16 hi + fp16 lo (x = hi + lo/2048) and
+// issues A_hi.[B_hi|B_lo] as ONE N = 2 NT MMA into [D0|D1] plus A_lo.B_hi into D1 (out = D0 + D1/2048).
+// Epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> split to fp16 hi/lo -> 256-bit global stores.
+//
+// Measured facts this design rests on (tools/umma_bench.cu, profiles/r01_umma_microbench.txt):
+//   * one tcgen05.mma M=128 K=16 costs max(32 + N/4, N/2) cycles: operands are read from shared memory at 128 B/cycle
+//     (4 KB of A + 32 N bytes of B) unless the tensor pipe (N/2) is slower; N >= 128 reaches the tensor peak, N = 48
+//     is shared-memory bound at 54 %.  M = 64 costs the same as M = 128.  A from TMEM would remove the 32 cycles.
+//   * accumulating into the same TMEM tile back to back costs nothing extra; swizzle mode of A / B and row-shifted
+//     start addresses cost nothing; the swizzle is a function of the absolute shared-memory address (row shifts
+//     need no base-offset field).
+//   * a single issuing lane sustains ~70 cycles per MMA once its descriptor arithmetic is included: the loops below
+//     keep descriptors as 32-bit low words with hoisted high words, unroll m-tiles at compile time and use two
+//     issuer warps in the halo kernel.
+//   * 16-byte epilogue stores are bound by the request rate (one half-filled sector each): 256-bit STG/LDG.
 // Replaces cuDNN conv + BatchNorm + ReLU + residual add (4 launches, 4 HBM round trips) of
 // regressor/human_shape/models/backbone/hrnet.py and torchvision BasicBlock / Bottleneck.
 #include <cmath>
@@ -382,19 +399,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 }
 
 // =================================================================================================
-// 3x3 stride-1 convolutions: "halo-resident" variant.
+// 3x3 convolutions, "halo-resident" variant.
 //
-// The per-tap variant above re-reads every input pixel 9 times from L2 (one shifted box per tap) and is
-// L2-bandwidth bound (ncu: ~5.5 TB/s of L2->SM traffic, tensor pipe 15 %).  Here the input of a
-// super-tile (a band of R output rows, or TN whole small images) is loaded ONCE per 16/32/64-channel group,
-// with its 1-pixel halo (TMA zero-fills the image border = the padding), into shared memory as UNSWIZZLED
-// 8-channel planes:  plane[k8][position][8 x fp16], position = (n * Hb + row) * Wp + col on the padded grid.
-// In that layout a row of the MMA A operand is 16 contiguous bytes at pitch 16, so the operand of tap
-// (ky, kx) for output positions o .. o+127 is simply the same plane read from position o + ky * Wp + kx:
-// all 9 taps x MT m-tiles are addressed by moving the start address of a no-swizzle K-major UMMA
-// descriptor (LBO = plane stride, SBO = 128 B).  Outputs are computed for the Wp - W padding columns too
-// (and discarded by the epilogue); in exchange activations cross L2 ~1.2-1.5x instead of 9x, and the
-// weights of one (tap, channel group) are shared by up to 5 m-tiles held in TMEM at once.
+// The per-tap variant re-reads every input pixel 9 times from L2 (one shifted box per tap; ncu: L2 52 %, tensor pipe
+// 15 %) and, for stride 2, is bound by the TMA unit's sector requests (each gathered pixel is its own 32..96-byte
+// request, 2.25x per pixel).  Here the input of a work item (a band of R output rows of one image, or TN whole small
+// images) is loaded ONCE per channel group by TMA, with its halo (out-of-image rows / columns are zero-filled = the
+// padding), as K-major swizzled rows  slice[position][KCH channels],  position = (n * Hb + row) * Wp + col  on the
+// padded grid.  The A operand of tap (ky, kx) for output positions o .. o+127 is the same slice read from position
+// o + ky * Wp + kx: all 9 taps x MT m-tiles are addressed by moving the start address of the UMMA descriptor by whole
+// rows (legal for any row count: the hardware swizzle is a function of the absolute address).  Stride 2 keeps four
+// parity planes (row parity x column parity) of the input per slice; tap (ky, kx) reads plane (ky != 1, kx != 1) at
+// position o (+ Wp for ky == 2) (+ 1 for kx == 2).  Outputs are computed for the padding columns too (and discarded
+// by the epilogue); in exchange activations cross L2 ~1.3x instead of 9x and the weights of one (tap, channel group)
+// are shared by up to 4 m-tiles held in TMEM at once (C = 48: all 27 weight blocks stay resident in shared memory).
 struct alignas(64) HaloParams {
   CUtensorMap a_hi[4], a_lo[4];  // stride 1: [0] = (C, W, H, N); stride 2: the four parity views [row parity * 2 + column
                                  // parity] of the input, each (C, W/2, H/2, N); box (KCH, Wp, Hb, TN), swizzled rows
