@@ -269,6 +269,10 @@ struct FuseParams {
 // CH = 8: 128-bit accesses; CH = 16: 256-bit accesses (rows 32-byte aligned), half the memory requests.
 template <int CH>
 __global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
+  // programmatic dependent launch (see conv_umma.cu): this grid may be scheduled while the producer of its inputs is
+  // draining, and lets the next launch do the same; the wait returns once every earlier grid has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int cg = p.C / CH;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long pix = idx / cg;
@@ -325,12 +329,24 @@ int launch_fuse(const ActView *ins, const int *shifts, int n_in, const ActView &
   };
   bool wide = out.C % 16 == 0 && al32(out);
   for (int i = 0; i < n_in; ++i) wide = wide && al32(ins[i]);
+  static const bool pdl = []() { const char *e = getenv("SHAPY_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (wide) {
     long long total = (long long)out.N * out.H * out.W * (out.C / 16);
-    fuse_kernel<16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    cfg.gridDim = dim3((unsigned)((total + 255) / 256));
+    SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, fuse_kernel<16>, p));
   } else {
     long long total = (long long)out.N * out.H * out.W * (out.C / 8);
-    fuse_kernel<8><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    cfg.gridDim = dim3((unsigned)((total + 255) / 256));
+    SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, fuse_kernel<8>, p));
   }
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;

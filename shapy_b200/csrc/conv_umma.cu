@@ -38,6 +38,7 @@
 // Replaces cuDNN conv + BatchNorm + ReLU + residual add (4 launches, 4 HBM round trips) of
 // regressor/human_shape/models/backbone/hrnet.py and torchvision BasicBlock / Bottleneck.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -931,9 +932,14 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   const int maxshift = stride == 1 ? 2 * Wp + 2 : Wp + 1;
   if (Wp > 256) return false;
   struct Cfg { int NT, TN, R, MT, Hb, bands, n_super, bres; double cost; } best = {0, 0, 0, 0, 0, 0, 0, 0, 1e30};
-  const double sm_count = 148.0, l2_bpc = 19.6;   // measured ~5.5 TB/s of L2->SM traffic = 19.6 B/cycle/SM
+  int f_nt = 0, f_tn = 0, f_r = 0;   // experiments: SHAPY_HALO_FORCE="NT,TN,R" pins the tile configuration
+  if (const char *e = getenv("SHAPY_HALO_FORCE")) sscanf(e, "%d,%d,%d", &f_nt, &f_tn, &f_r);
+  // L2 -> SM bytes per cycle per SM the TMA loads can count on: the per-tap C=192 layer moves 296 MB in 30 us = 9.9 TB/s
+  // = 41 B/cycle/SM at the 1.63 GHz these kernels run at (the first-generation kernels only reached 19.6, which made
+  // the model avoid streamed weights: C=96 with R=4 / MT=1 / double-buffered accumulators is 9 % faster than R=7 / MT=2)
+  const double sm_count = 148.0, l2_bpc = []() { const char *e = getenv("SHAPY_HALO_L2BPC"); return e ? atof(e) : 40.0; }();
   for (int NT = 128; NT >= 16; NT -= 16) {
-    if (w.cout % NT) continue;
+    if (w.cout % NT || (f_nt && NT != f_nt)) continue;
     const int mt_max = std::min(8, 512 / (NT * parts));
     if (mt_max < 1) continue;
     const int n_tiles = w.cout / NT;
@@ -941,6 +947,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     const size_t b_all = b_blk * 9 * (w.cin / kch);
     const bool bres = n_tiles == 1 && b_all <= 120 * 1024;
     auto consider = [&](int TN, int R) {
+      if (f_nt && (TN != f_tn || R != f_r)) return;
       const int Hb = R + hpad;
       const int bands = ceil_div(H, R);
       const int P = TN * Hb * Wp;
