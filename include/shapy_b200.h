@@ -200,6 +200,28 @@ double shapy_hrnet_flops(const shapy_hrnet_t *p, int batch, int height, int widt
 int shapy_conv_test(const shapy_conv_desc_t *conv, const float *x, const float *res, int batch, int height,
                     int width, int relu, int mode, int engine, float *y, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input stage: uint8 full images + crop windows -> normalised fp32 NCHW crops.
+ * Replaces, per detected person, the reference's CPU chain
+ *   read_img        regressor/human_shape/utils/img_utils.py:57-61         (uint8 -> float32 / 255, clip)
+ *   crop            regressor/human_shape/utils/transf_utils.py:51-96      (window [ul, br), zero padding,
+ *                                                                           cv2.resize INTER_LINEAR to size x size)
+ *   ToTensor + Normalize  regressor/human_shape/data/transforms/transforms.py:710-733  (clamp [0,1], (x - mean) / std)
+ * The window corners are computed by the host exactly as transf_utils.py:41-56 does (float32 matrix inverse and
+ * integer truncation; shapy_b200/preprocess.py mirrors it) and passed in the descriptor.
+ *   images : device, all uint8 HxWx3 (RGB, row-major) images of the batch back to back
+ *   descs  : device, one per output crop (several crops may name the same image)
+ *   mean, stdv : host, 3 floats each
+ *   out    : device (B, 3, size, size) fp32 */
+typedef struct shapy_image_desc_t {
+  long long offset;        /* byte offset of the image inside `images` */
+  int height, width;       /* image extent */
+  int ul_x, ul_y;          /* window upper-left corner (inclusive), may be negative */
+  int br_x, br_y;          /* window bottom-right corner (exclusive), may exceed the image */
+} shapy_image_desc_t;
+int shapy_preprocess_forward(const unsigned char *images, const shapy_image_desc_t *descs, int batch, int size,
+                             const float *mean, const float *stdv, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,11 @@ class Slot(C.Structure):
     _fields_ = [('channels', c_int), ('div', c_int)]
 
 
+class ImageDesc(C.Structure):
+    _fields_ = [('offset', C.c_longlong), ('height', c_int), ('width', c_int), ('ul_x', c_int), ('ul_y', c_int),
+                ('br_x', c_int), ('br_y', c_int)]
+
+
 OP_STEM, OP_CONV, OP_FUSE, OP_POOL = 0, 1, 2, 3
 
 _SIGS = {
@@ -79,6 +84,8 @@ _SIGS = {
     'shapy_hrnet_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'shapy_hrnet_read_slot': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'shapy_hrnet_flops': (C.c_double, [c_void_p, c_int, c_int, c_int]),
+    'shapy_preprocess_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), c_void_p,
+                                         c_void_p]),
     'shapy_conv_test': (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p]),
 }

@@ -18,6 +18,8 @@ Everything written here is a small fixture that travels to the GPU box, where
   ref_hrnet.npz         reference HighResolutionNet outputs on the seeded synthetic checkpoint
   hrnet_keys.json       the 1 967 state-dict keys/shapes of the reference backbone (sha256 + list)
   ref_measure.json      oracle/measure (quirk-faithful op.cu emulation) results on the 4 real bodies
+  preprocess.npz        reference input stage (transf_utils.crop with cv2 + ToTensor + Normalize) on seeded uint8 images:
+                        crop windows, crops with OpenCV's portable path (IPP off) and with this container's IPP build
 """
 import hashlib
 import json
@@ -131,8 +133,55 @@ def hrnet_fixture():
     print('ref_hrnet.npz', out['concat'].shape, float(out['concat'].abs().mean()), len(keys), digest[:12])
 
 
+def preprocess_fixture():
+    """Runs the reference's own crop() (regressor/human_shape/utils/transf_utils.py, loaded by path; cv2 is present in the
+    build container) followed by the ToTensor / Normalize arithmetic of data/transforms/transforms.py:603-624,710-733."""
+    import importlib.util
+    import cv2
+    import torchvision.transforms.functional as F
+    spec = importlib.util.spec_from_file_location('ref_transf_utils', os.path.join(ref_shim.HS, 'utils', 'transf_utils.py'))
+    tu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tu)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]      # config/datasets_defaults.py:37-38
+    rng = np.random.default_rng(20240923)
+    out = {'mean': np.float32(mean), 'std': np.float32(std)}
+    cases = [  # (H, W, center, scale, size): inside, overhanging every border, strong down- and up-scaling
+        (96, 128, (64.0, 48.0), 0.40, 64), (96, 128, (5.5, 90.25), 0.55, 64), (120, 90, (80.0, 10.0), 0.9, 32),
+        (70, 70, (35.0, 35.0), 0.12, 64), (150, 200, (100.7, 75.2), 1.35, 32), (64, 48, (24.0, 32.0), 0.32, 64),
+    ]
+    for i, (H, W, center, scale, size) in enumerate(cases):
+        # image-like content: smooth gradients plus noise, uint8
+        yy, xx = np.mgrid[0:H, 0:W]
+        img = np.stack([(xx * 255.0 / W), (yy * 255.0 / H), ((xx + yy) * 255.0 / (H + W))], -1)
+        img = np.clip(img + rng.normal(0, 25, img.shape), 0, 255).astype(np.uint8)
+        imgf = np.clip(img.astype(np.float32) / 255.0, 0, 1)                      # read_img, img_utils.py:57-61
+        c = np.array(center, dtype=np.float32)
+        res = {}
+        for tag, ipp in (('portable', False), ('ipp', True)):
+            cv2.ipp.setUseIPP(ipp)
+            crop = tu.crop(imgf, c, scale, [size, size])
+            t = F.to_tensor(crop)
+            t = torch.clamp(t, 0, 1)
+            res[tag] = F.normalize(t, mean=mean, std=std).numpy()
+        cv2.ipp.setUseIPP(True)
+        ul = np.array(tu.transform([1, 1], c, scale, [size, size], invert=1)) - 1
+        br = np.array(tu.transform([size + 1, size + 1], c, scale, [size, size], invert=1)) - 1
+        out[f'img{i}'] = img
+        out[f'center{i}'] = c
+        out[f'scale{i}'] = np.float64(scale)
+        out[f'size{i}'] = np.int64(size)
+        out[f'ul{i}'] = ul.astype(np.int64)
+        out[f'br{i}'] = br.astype(np.int64)
+        out[f'out{i}'] = res['portable']
+        out[f'ipp_dev{i}'] = np.float64(np.abs(res['portable'] - res['ipp']).max())   # this container's IPP build vs portable
+    out['n'] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(G, 'preprocess.npz'), **out)
+    print('preprocess.npz', os.path.getsize(os.path.join(G, 'preprocess.npz')), 'bytes; max |portable - ipp| =',
+          max(float(out[f'ipp_dev{i}']) for i in range(len(cases))))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet']
+    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess']
     torch.set_num_threads(8)
     if 'body' in which:
         body_fixture()
@@ -142,3 +191,5 @@ if __name__ == '__main__':
         head_fixture()
     if 'hrnet' in which:
         hrnet_fixture()
+    if 'preprocess' in which:
+        preprocess_fixture()
