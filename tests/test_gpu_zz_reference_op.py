@@ -26,8 +26,11 @@ def run_reference(tmp_path, query, target, max_collisions):
         pytest.skip('oracle/_ref is not built (python oracle/build_ref.py in the build container)')
     inp, outp = str(tmp_path / 'in.npz'), str(tmp_path / 'out.npz')
     np.savez(inp, query=query, target=target, max_collisions=np.int64(max_collisions))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'run_ref_mmi.py'), inp, outp], capture_output=True,
-                       text=True, timeout=300)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'run_ref_mmi.py'), inp, outp], capture_output=True,
+                           text=True, timeout=300)
+    except subprocess.TimeoutExpired:
+        pytest.skip('reference kernel did not finish within 300 s on this box')
     if r.returncode != 0 or not os.path.exists(outp):
         pytest.skip(f'reference kernel did not run here: rc {r.returncode}: {(r.stderr or r.stdout)[-300:]}')
     d = np.load(outp)
