@@ -222,6 +222,17 @@ typedef struct shapy_image_desc_t {
 int shapy_preprocess_forward(const unsigned char *images, const shapy_image_desc_t *descs, int batch, int size,
                              const float *mean, const float *stdv, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * B2A attribute head: betas -> attribute ratings with the male / female regressors.
+ * Replaces regressor/human_shape/models/common/iterative_regressor.py:761-776 and
+ * attributes/attributes/attributes_betas/polynomial.py:61-69,137-140 (degree-2 polynomial features + Linear).
+ *   betas  : device (B, num_betas) fp32        gender : device (B) int32, 0 = male, 1 = female, other = row of zeros
+ *   w_*    : device (num_outputs, num_betas + num_betas (num_betas + 1) / 2) fp32 row-major (Linear.weight)
+ *   b_*    : device (num_outputs) fp32         out    : device (B, num_outputs) fp32 */
+int shapy_b2a_forward(const float *betas, const int *gender, const float *w_male, const float *b_male,
+                      const float *w_female, const float *b_female, int batch, int num_betas, int num_outputs, float *out,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's B2A attribute head.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
+
+Reference:
+    Polynomial            attributes/attributes/attributes_betas/polynomial.py:21-140
+        _combinations     55-59   itertools.combinations_with_replacement(range(n), i) for i in 1..degree
+        build_polynomial_coeffs 61-69   A = cat([prod(X[:, indices_k], -1) for k in range(degree)], -1)
+        forward           137-140 linear(A)
+    per-gender routing    regressor/human_shape/models/common/iterative_regressor.py:761-776
+        genders 'm' -> b2a_males, 'f' -> b2a_females, anything else -> a row of zeros
+
+Pinned: tests/golden/b2a.npz holds outputs of the reference's own Polynomial module (loaded by path in the build
+container by tools/make_golden.py) on seeded weights and betas; tests/test_attributes_cpu.py checks this file
+against them.
+"""
+from itertools import combinations_with_replacement
+
+import numpy as np
+
+
+def feature_indices(n: int, degree: int = 2):
+    """The index tuples in the order polynomial.py:38-59 registers them (degree 1 first, then degree 2)."""
+    out = []
+    for d in range(1, degree + 1):
+        out += list(combinations_with_replacement(range(n), d))
+    return out
+
+
+def polynomial_features(x: np.ndarray, degree: int = 2) -> np.ndarray:
+    """(B, n) -> (B, n_feat) float32, polynomial.py:61-69."""
+    x = np.asarray(x, np.float32)
+    cols = [np.prod(x[:, list(idx)], axis=-1, dtype=np.float32) for idx in feature_indices(x.shape[1], degree)]
+    return np.stack(cols, -1).astype(np.float32)
+
+
+def polynomial_forward(x, weight, bias, degree: int = 2) -> np.ndarray:
+    """polynomial.py:137-140: Linear on the features (float64 accumulation; the bar against fp32 GEMMs is 1e-6 relative)."""
+    a = polynomial_features(x, degree).astype(np.float64)
+    return (a @ np.asarray(weight, np.float64).T + np.asarray(bias, np.float64)).astype(np.float32)
+
+
+def b2a_by_gender(betas, genders, male, female) -> np.ndarray:
+    """iterative_regressor.py:761-776.  genders: sequence of str or None; male / female: (weight, bias)."""
+    betas = np.asarray(betas, np.float32)
+    g = np.array([x.lower()[0] if (x is not None and x != '') else 'n' for x in genders])
+    out = np.zeros((betas.shape[0], np.asarray(male[0]).shape[0]), np.float32)
+    m, f = np.where(g == 'm')[0], np.where(g == 'f')[0]
+    if len(m):
+        out[m] = polynomial_forward(betas[m], *male)
+    if len(f):
+        out[f] = polynomial_forward(betas[f], *female)
+    return out

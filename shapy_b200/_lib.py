@@ -86,6 +86,8 @@ _SIGS = {
     'shapy_hrnet_flops': (C.c_double, [c_void_p, c_int, c_int, c_int]),
     'shapy_preprocess_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), c_void_p,
                                          c_void_p]),
+    'shapy_b2a_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  c_void_p]),
     'shapy_conv_test': (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p]),
 }

@@ -3,8 +3,9 @@ regressor/human_shape/models/common/iterative_regressor.py (ctor 40-209, forward
 
 Same constructor, registered buffers (`{name}_idxs`, `{name}_mean`, `param_mean`), sub-module names
 (backbone, regressor, model, global_rot_decoder, body_pose_decoder, body_measurements) and output dict.
-Inference only: the compute is five C-ABI calls (HRNet, head, 6D decode, SMPL-X, measurements).
-B2A / A2B attribute heads are "next" rows and are not built.
+Inference only: the compute is five C-ABI calls (HRNet, head, 6D decode, SMPL-X, measurements), plus one for the
+B2A attribute head when its two checkpoints are configured (iterative_regressor.py:146-171, 761-776).  The A2B head
+(attributes -> betas, a second body-model pass) is not built.
 """
 import os.path as osp
 from collections import defaultdict
@@ -13,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops as _ops
+from ....attributes import B2A, b2a_forward, gender_codes
 from ....body_measurements import BodyMeasurements
 from ..backbone.build import build_backbone
 from ..body_models.utils import KeypointTensor
@@ -67,7 +69,19 @@ class HMRLikeRegressor(nn.Module):
             if lm is not None:
                 cfg['landmarks'] = lm
             self.body_measurements = BodyMeasurements(cfg)
-        self.use_b2a, self.use_a2b = False, False
+        # betas -> attributes regressors, one per gender (iterative_regressor.py:146-171)
+        b2a_m = osp.expandvars(network_cfg.get('b2a_males_checkpoint', '') or '')
+        b2a_f = osp.expandvars(network_cfg.get('b2a_females_checkpoint', '') or '')
+        self.use_b2a = bool(network_cfg.get('use_b2a', False)) and osp.exists(b2a_m) and osp.exists(b2a_f)
+        if self.use_b2a:
+            self.b2a_males = B2A.load_from_checkpoint(b2a_m)
+            self.b2a_females = B2A.load_from_checkpoint(b2a_f)
+            for mod in (self.b2a_males, self.b2a_females):
+                for p in mod.parameters():
+                    p.requires_grad = False
+        if network_cfg.get('use_a2b', False) and osp.exists(osp.expandvars(network_cfg.get('a2b_males_checkpoint', '') or '')):
+            raise NotImplementedError('shapy_b200: the A2B head (iterative_regressor.py:173-204, 778-852) is not built')
+        self.use_a2b = False
 
     # properties of the reference class
     param_dim = property(lambda self: self._param_dim)
@@ -134,5 +148,8 @@ class HMRLikeRegressor(nn.Module):
             out_params.update(measurements=meas_dict)
         out_params['stage_keys'] = stage_keys
         out_params[stage_keys[-1]]['proj_joints'] = proj_joints
+        if self.use_b2a:
+            codes = torch.from_numpy(gender_codes(targets, batch_size))
+            out_params['attributes'] = b2a_forward(merged['betas'], codes, self.b2a_males, self.b2a_females)
         out_params['losses'] = {}
         return out_params

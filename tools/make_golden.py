@@ -18,6 +18,7 @@ Everything written here is a small fixture that travels to the GPU box, where
   ref_hrnet.npz         reference HighResolutionNet outputs on the seeded synthetic checkpoint
   hrnet_keys.json       the 1 967 state-dict keys/shapes of the reference backbone (sha256 + list)
   ref_measure.json      oracle/measure (quirk-faithful op.cu emulation) results on the 4 real bodies
+  b2a.npz               reference Polynomial (B2A head) outputs with seeded male / female weights, routed by gender
   preprocess.npz        reference input stage (transf_utils.crop with cv2 + ToTensor + Normalize) on seeded uint8 images:
                         crop windows, crops with OpenCV's portable path (IPP off) and with this container's IPP build
 """
@@ -180,8 +181,50 @@ def preprocess_fixture():
           max(float(out[f'ipp_dev{i}']) for i in range(len(cases))))
 
 
+def b2a_fixture():
+    """Runs the reference's own Polynomial module (attributes/attributes/attributes_betas/polynomial.py, loaded by path behind
+    a stub of attributes.utils.typing) with seeded male / female weights, and routes by gender exactly as
+    regressor/human_shape/models/common/iterative_regressor.py:761-776 does."""
+    import importlib.util
+    import types
+    from loguru import logger
+    logger.remove()
+    for name in ('attributes', 'attributes.utils', 'attributes.utils.typing'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules['attributes.utils.typing'].Tensor = torch.Tensor
+    sys.modules['attributes.utils.typing'].Array = np.ndarray
+    spec = importlib.util.spec_from_file_location(
+        'ref_polynomial', os.path.join(REF, 'attributes', 'attributes', 'attributes_betas', 'polynomial.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(31)
+    males, females = mod.Polynomial(10, 15, degree=2), mod.Polynomial(10, 15, degree=2)
+    for p in (males, females):                      # ratings live in [1, 5]: give the synthetic heads that scale
+        with torch.no_grad():
+            p.linear.weight.mul_(0.5)
+            p.linear.bias.copy_(torch.rand(15) * 4 + 1)
+    betas = torch.randn(9, 10) * 1.5
+    gender_strs = ['male', 'Female', 'f', '', None, 'M', 'neutral', 'female', 'm']
+    genders = np.array([x.lower()[0] if (x is not None and x != '') else 'n' for x in gender_strs])
+    gm, gf = np.where(genders == 'm')[0], np.where(genders == 'f')[0]
+    with torch.no_grad():
+        am, af = males(betas[gm, :]), females(betas[gf, :])
+        attributes = torch.zeros(betas.shape[0], am.shape[1])
+        attributes[gm, :] = am
+        attributes[gf, :] = af
+    np.savez_compressed(
+        os.path.join(G, 'b2a.npz'), betas=betas.numpy(), genders=np.array([g if g is not None else '<none>' for g in gender_strs]),
+        w_male=males.linear.weight.detach().numpy(), b_male=males.linear.bias.detach().numpy(),
+        w_female=females.linear.weight.detach().numpy(), b_female=females.linear.bias.detach().numpy(),
+        indices_000=males.indices_000.numpy(), indices_001=males.indices_001.numpy(), attributes=attributes.numpy())
+    print('b2a.npz', os.path.getsize(os.path.join(G, 'b2a.npz')), 'bytes')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess']
+    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess', 'b2a']
     torch.set_num_threads(8)
     if 'body' in which:
         body_fixture()
@@ -193,3 +236,5 @@ if __name__ == '__main__':
         hrnet_fixture()
     if 'preprocess' in which:
         preprocess_fixture()
+    if 'b2a' in which:
+        b2a_fixture()
