@@ -233,6 +233,20 @@ int shapy_b2a_forward(const float *betas, const int *gender, const float *w_male
                       const float *w_female, const float *b_female, int batch, int num_betas, int num_outputs, float *out,
                       void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metric: translation-aligned point-to-point error through sparse point regressors
+ * ("P2P-20k", also plain v2v with identity regressors).  Replaces regressor/human_shape/utils/metrics.py:368-456
+ * (v2vhdError.__call__) and regressor/hbw_evaluation/evaluate_hbw.py:44-58,147-151.
+ *   in_* / tg_* : device CSR (row_ptr int32 [P+1], col int32 [nnz], val fp32 [nnz]) of the P x V1 / P x V2 regressors
+ *   input_vertices (B, V1, 3), target_vertices (B, V2, 3) : device fp32
+ *   align : 1 = translate by mean(target points) - mean(input points) (metrics.py:431-439)
+ *   error (B, P), mean_error (B) : device fp32      workspace : >= shapy_p2p_workspace_bytes(B, P) */
+size_t shapy_p2p_workspace_bytes(int batch, int num_points);
+int shapy_p2p_error(const int *in_row_ptr, const int *in_col, const float *in_val, const int *tg_row_ptr, const int *tg_col,
+                    const float *tg_val, const float *input_vertices, const float *target_vertices, int batch, int num_points,
+                    int num_input_vertices, int num_target_vertices, int align, float *error, float *mean_error, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,5 @@
 """Builds the C restatement (oracle/mmi_oracle.c) into oracle/_build/libmmi_oracle.so and the host-compiled copy of
-the input-stage pixel function and of the B2A output function (oracle/preprocess_host.cpp, oracle/attributes_host.cpp)
+the input-stage pixel function and of the B2A output function (oracle/preprocess_host.cpp, oracle/attributes_host.cpp, oracle/metrics_host.cpp)
 into oracle/_build/.
 
 TEST INFRASTRUCTURE ONLY.  Building the checker is not using it: __graft_entry__.build()
@@ -21,6 +21,7 @@ def build(force: bool = False) -> str:
                                src, '-lm'])
     build_preprocess_host(force)
     build_attributes_host(force)
+    build_metrics_host(force)
     return out
 
 
@@ -42,6 +43,18 @@ def build_attributes_host(force: bool = False) -> str:
     src = os.path.join(_HERE, 'attributes_host.cpp')
     hdr = os.path.join(os.path.dirname(_HERE), 'shapy_b200', 'csrc', 'attributes.cuh')
     out = os.path.join(out_dir, 'libattributes_host.so')
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-fno-fast-math', '-shared', '-fPIC', '-o', out, src])
+    return out
+
+
+def build_metrics_host(force: bool = False) -> str:
+    out_dir = os.path.join(_HERE, '_build')
+    os.makedirs(out_dir, exist_ok=True)
+    src = os.path.join(_HERE, 'metrics_host.cpp')
+    hdr = os.path.join(os.path.dirname(_HERE), 'shapy_b200', 'csrc', 'metrics.cuh')
+    out = os.path.join(out_dir, 'libmetrics_host.so')
     newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
     if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
         subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-fno-fast-math', '-shared', '-fPIC', '-o', out, src])

@@ -19,6 +19,7 @@ Everything written here is a small fixture that travels to the GPU box, where
   hrnet_keys.json       the 1 967 state-dict keys/shapes of the reference backbone (sha256 + list)
   ref_measure.json      oracle/measure (quirk-faithful op.cu emulation) results on the 4 real bodies
   b2a.npz               reference Polynomial (B2A head) outputs with seeded male / female weights, routed by gender
+  p2p.npz               reference v2vhdError (P2P metric) outputs on seeded sparse point regressors and meshes
   preprocess.npz        reference input stage (transf_utils.crop with cv2 + ToTensor + Normalize) on seeded uint8 images:
                         crop windows, crops with OpenCV's portable path (IPP off) and with this container's IPP build
 """
@@ -223,8 +224,71 @@ def b2a_fixture():
     print('b2a.npz', os.path.getsize(os.path.join(G, 'b2a.npz')), 'bytes')
 
 
+def p2p_fixture():
+    """Runs the reference's own v2vhdError (regressor/human_shape/utils/metrics.py:368-456, loaded by path behind stubs of
+    open3d / .np_utils / .typing) on seeded sparse point regressors (3 barycentric weights per point) and meshes, in
+    float64 on the CPU as the evaluator does (evaluation.py:258-260)."""
+    import importlib.util
+    import pickle
+    import tempfile
+    import types
+    import scipy.sparse as sp
+    from loguru import logger
+    logger.remove()
+    for name in ('open3d', 'ref_hs', 'ref_hs.utils', 'ref_hs.utils.np_utils', 'ref_hs.utils.typing'):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    sys.modules['ref_hs.utils.np_utils'].np2o3d_pcl = None
+    for n in ('Tensor', 'Array', 'IntList'):
+        setattr(sys.modules['ref_hs.utils.typing'], n, object)
+    spec = importlib.util.spec_from_file_location('ref_hs.utils.metrics', os.path.join(ref_shim.HS, 'utils', 'metrics.py'))
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = 'ref_hs.utils'
+    sys.modules['ref_hs.utils.metrics'] = mod
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(77)
+    P, V1, V2, B = 700, 400, 250, 3
+
+    def regressor(V):
+        cols = rng.integers(0, V, (P, 3))
+        w = rng.dirichlet([1, 1, 1], P)
+        # float32-representable weights stored as float64, the dtype of the reference's regressor pickles (the evaluator
+        # multiplies them with .double() vertices)
+        return sp.csr_matrix((w.reshape(-1).astype(np.float32).astype(np.float64), (np.repeat(np.arange(P), 3), cols.reshape(-1))),
+                             shape=(P, V))
+    r_in, r_tg = regressor(V1), regressor(V2)
+    r_in.sum_duplicates()
+    r_tg.sum_duplicates()
+    tmp = tempfile.mkdtemp()
+    paths = []
+    for name, r in (('in', r_in), ('tg', r_tg)):
+        paths.append(os.path.join(tmp, name + '.pkl'))
+        with open(paths[-1], 'wb') as f:
+            pickle.dump(r, f)
+    v_in = (rng.normal(0, 0.3, (B, V1, 3)) + [0.1, -0.2, 0.05]).astype(np.float32)
+    v_tg = (rng.normal(0, 0.3, (B, V2, 3)) + [-0.3, 0.4, 0.0]).astype(np.float32)
+    out = {}
+    for align in (True, False):
+        metric = mod.v2vhdError(paths[0], paths[1], align=align)
+        if align:
+            mean, err = metric(torch.from_numpy(v_in).double(), torch.from_numpy(v_tg).double())
+        else:       # metrics.py:449-452 only defines t under `if self.align`: the unaligned variant is the same formula with t = 0
+            a = metric.sparse_batch_mm(metric.input_point_regressor.double(), torch.from_numpy(v_in).double())
+            c = metric.sparse_batch_mm(metric.target_point_regressor.double(), torch.from_numpy(v_tg).double())
+            err = torch.sqrt(torch.pow(a - c, 2).sum(axis=-1))
+            mean = err.mean(1)
+        out['mean_aligned' if align else 'mean_raw'] = mean.numpy()
+        out['error_aligned' if align else 'error_raw'] = err.numpy()
+    for name, r in (('in', r_in), ('tg', r_tg)):
+        out[f'{name}_row_ptr'], out[f'{name}_col'], out[f'{name}_val'] = (r.indptr.astype(np.int32), r.indices.astype(np.int32),
+                                                                             r.data.astype(np.float32))
+    np.savez_compressed(os.path.join(G, 'p2p.npz'), v_in=v_in, v_tg=v_tg, **out)
+    print('p2p.npz', os.path.getsize(os.path.join(G, 'p2p.npz')), 'bytes; mean aligned error', out['mean_aligned'])
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess', 'b2a']
+    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess', 'b2a', 'p2p']
     torch.set_num_threads(8)
     if 'body' in which:
         body_fixture()
@@ -238,3 +302,5 @@ if __name__ == '__main__':
         preprocess_fixture()
     if 'b2a' in which:
         b2a_fixture()
+    if 'p2p' in which:
+        p2p_fixture()
