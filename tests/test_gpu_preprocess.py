@@ -1,5 +1,5 @@
 """Input stage kernel (shapy_preprocess_forward through shapy_b200.preprocess.InputStage) against the reference's own
-crops (tests/golden/preprocess.npz) and the numpy oracle.  Named zz so it runs after the hot-path parity tests."""
+crops (tests/golden/preprocess.npz) and the numpy oracle."""
 import os
 
 import numpy as np
