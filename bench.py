@@ -64,7 +64,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in o.split(',')])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)     # nvidia-smi itself takes ~0.1 s: 5-7 samples per second of timed region
 
     def __enter__(self):
         self.t.start()
