@@ -174,7 +174,13 @@ typedef struct {
   int n_in;
   int fuse_in[4];
   int fuse_shift[4];
+  /* Execution lane (0..SHAPY_MAX_LANES-1).  Ops of one lane run in program order on one CUDA stream; ops of
+   * different lanes may run concurrently (the independent branches of a HighResolutionModule, reference
+   * hrnet.py:175-193).  The executor derives every cross-lane ordering itself from the slots an op reads and
+   * writes (RAW, WAR and WAW), so the lane is a scheduling hint only: any assignment gives the serial result. */
+  int lane;
 } shapy_op_t;
+enum { SHAPY_MAX_LANES = 4 };
 
 typedef struct {
   int channels;      /* total channels of the slot */

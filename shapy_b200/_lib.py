@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
 class Op(C.Structure):
     _fields_ = [('kind', c_int), ('conv', c_int), ('in_slot', c_int), ('out_slot', c_int), ('out_coff', c_int),
                 ('res_slot', c_int), ('relu', c_int), ('n_in', c_int), ('fuse_in', c_int * 4),
-                ('fuse_shift', c_int * 4)]
+                ('fuse_shift', c_int * 4), ('lane', c_int)]
 
 
 class Slot(C.Structure):

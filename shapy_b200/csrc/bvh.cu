@@ -344,11 +344,8 @@ extern "C" int shapy_mmi_forward(const float *query, const float *target, int B,
   SHAPY_LAUNCH_CHECK();
   SHAPY_CUDA_TRY(cudaMemsetAsync(collision_bcs, 0, n_slots * 6 * sizeof(float), st));
   const size_t smem = (size_t)npow2 * 4 + (size_t)npow2 * 2;
-  static bool attr = false;
-  if (!attr) {
-    SHAPY_CUDA_TRY(cudaFuncSetAttribute(bvh_prepare_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  SHAPY_CUDA_TRY(set_max_dynamic_smem(bvh_prepare_kernel<unsigned short>, 200 * 1024, attr_done));
   bvh_prepare_kernel<unsigned short><<<B, 1024, smem, st>>>(target, F, npow2, w);
   SHAPY_LAUNCH_CHECK();
   if (F > 1) {

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,20 @@ void count_launch(int n = 1);
       return SHAPY_ERR_ARG;                                                               \
     }                                                                                     \
   } while (0)
+
+// cudaFuncSetAttribute applies to the CURRENT device only: a process that drives several GPUs must configure the
+// kernel once per device, so the "already done" state is a per-device bit, not a process-wide flag.
+template <typename Kernel>
+static inline cudaError_t set_max_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long> &done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

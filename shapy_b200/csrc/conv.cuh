@@ -62,6 +62,6 @@ struct UmmaPlan;
 bool umma_supported(const ConvW &w, const ActView &in, const ActView &out);
 UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out, const ActView *res, bool relu);
 void umma_plan_destroy(UmmaPlan *p);
-int umma_plan_launch(const UmmaPlan *p, cudaStream_t st);
+int umma_plan_launch(const UmmaPlan *p, cudaStream_t st, bool pdl);   // pdl: programmatic dependent launch
 
 }  // namespace shapy

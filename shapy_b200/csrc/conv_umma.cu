@@ -1194,14 +1194,8 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
 
 void umma_plan_destroy(UmmaPlan *p) { delete p; }
 
-static bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("SHAPY_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-
 template <typename Kernel, typename Params>
-static int launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &params) {
+static int launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &params, bool pdl) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -1212,29 +1206,23 @@ static int launch_pdl(Kernel kernel, dim3 grid, int threads, size_t smem, cudaSt
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
   shapy::count_launch();
   return SHAPY_OK;
 }
 
 template <int KCH, bool SPLIT>
-static int launch_t(const UmmaPlan *pl, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SHAPY_CUDA_TRY(cudaFuncSetAttribute(conv_umma_kernel<KCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  return launch_pdl(conv_umma_kernel<KCH, SPLIT>, pl->grid, kThreads, pl->smem, st, pl->p);
+static int launch_t(const UmmaPlan *pl, cudaStream_t st, bool pdl) {
+  static std::atomic<unsigned long long> attr_done{0};
+  SHAPY_CUDA_TRY(set_max_dynamic_smem(conv_umma_kernel<KCH, SPLIT>, 227 * 1024, attr_done));
+  return launch_pdl(conv_umma_kernel<KCH, SPLIT>, pl->grid, kThreads, pl->smem, st, pl->p, pdl);
 }
 
 template <int KCH, bool SPLIT>
-static int launch_halo_t(const UmmaPlan *pl, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SHAPY_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+static int launch_halo_t(const UmmaPlan *pl, cudaStream_t st, bool pdl) {
+  static std::atomic<unsigned long long> attr_done{0};
+  SHAPY_CUDA_TRY(set_max_dynamic_smem(conv_halo_kernel<KCH, SPLIT>, 227 * 1024, attr_done));
   static const bool phases = getenv("SHAPY_CONV_PHASES") != nullptr;
   if (phases) {
     // debug: per-CTA cycle counters of each warp role's waits (synchronous, prints to stderr)
@@ -1273,28 +1261,28 @@ static int launch_halo_t(const UmmaPlan *pl, cudaStream_t st) {
     shapy::count_launch();
     return SHAPY_OK;
   }
-  return launch_pdl(conv_halo_kernel<KCH, SPLIT>, pl->grid, kHaloThreads, pl->smem, st, pl->hp);
+  return launch_pdl(conv_halo_kernel<KCH, SPLIT>, pl->grid, kHaloThreads, pl->smem, st, pl->hp, pdl);
 }
 
-int umma_plan_launch(const UmmaPlan *pl, cudaStream_t st) {
+int umma_plan_launch(const UmmaPlan *pl, cudaStream_t st, bool pdl) {
   if (pl->halo) {
     if (pl->split) {
-      if (pl->kch == 64) return launch_halo_t<64, true>(pl, st);
-      if (pl->kch == 32) return launch_halo_t<32, true>(pl, st);
-      return launch_halo_t<16, true>(pl, st);
+      if (pl->kch == 64) return launch_halo_t<64, true>(pl, st, pdl);
+      if (pl->kch == 32) return launch_halo_t<32, true>(pl, st, pdl);
+      return launch_halo_t<16, true>(pl, st, pdl);
     }
-    if (pl->kch == 64) return launch_halo_t<64, false>(pl, st);
-    if (pl->kch == 32) return launch_halo_t<32, false>(pl, st);
-    return launch_halo_t<16, false>(pl, st);
+    if (pl->kch == 64) return launch_halo_t<64, false>(pl, st, pdl);
+    if (pl->kch == 32) return launch_halo_t<32, false>(pl, st, pdl);
+    return launch_halo_t<16, false>(pl, st, pdl);
   }
   if (pl->split) {
-    if (pl->kch == 64) return launch_t<64, true>(pl, st);
-    if (pl->kch == 32) return launch_t<32, true>(pl, st);
-    return launch_t<16, true>(pl, st);
+    if (pl->kch == 64) return launch_t<64, true>(pl, st, pdl);
+    if (pl->kch == 32) return launch_t<32, true>(pl, st, pdl);
+    return launch_t<16, true>(pl, st, pdl);
   }
-  if (pl->kch == 64) return launch_t<64, false>(pl, st);
-  if (pl->kch == 32) return launch_t<32, false>(pl, st);
-  return launch_t<16, false>(pl, st);
+  if (pl->kch == 64) return launch_t<64, false>(pl, st, pdl);
+  if (pl->kch == 32) return launch_t<32, false>(pl, st, pdl);
+  return launch_t<16, false>(pl, st, pdl);
 }
 
 }  // namespace shapy

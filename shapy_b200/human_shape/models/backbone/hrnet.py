@@ -16,6 +16,7 @@ from .... import ops as _ops
 from ...._lib import OP_CONV, OP_FUSE, OP_POOL, OP_STEM
 
 BN_MOMENTUM = 0.1
+N_LANES = 4          # SHAPY_MAX_LANES of include/shapy_b200.h
 
 DEFAULT_STAGES = {  # regressor/human_shape/config/network_defaults.py:92-132
     'stage1': dict(num_modules=1, num_branches=1, num_blocks=(4,), num_channels=(64,), block='BOTTLENECK',
@@ -150,9 +151,14 @@ class _Graph:
     def __init__(self):
         self.convs, self.ops, self.tensors = [], [], []
         self.keep = set()
+        self.lane = 0       # execution lane of the ops emitted next (scheduling hint, see shapy_op_t.lane)
+
+    def on(self, lane):
+        self.lane = int(lane) % N_LANES
+        return self
 
     def tensor(self, channels, div):
-        self.tensors.append(dict(channels=channels, div=div))
+        self.tensors.append(dict(channels=channels, div=div, lane=self.lane))
         return len(self.tensors) - 1
 
     def _conv_entry(self, conv, bn):
@@ -168,18 +174,19 @@ class _Graph:
         if out is None:
             out = self.tensor(conv.out_channels, div)
         self.ops.append(dict(kind=OP_STEM if x < 0 else OP_CONV, conv=self._conv_entry(conv, bn), in_slot=x,
-                             out_slot=out, out_coff=out_coff, res_slot=-1 if res is None else res, relu=int(relu)))
+                             out_slot=out, out_coff=out_coff, res_slot=-1 if res is None else res, relu=int(relu),
+                             lane=self.lane))
         return out
 
     def fuse(self, ins, relu=True):
         t0 = self.tensors[ins[0][0]]
         out = self.tensor(t0['channels'], t0['div'] >> ins[0][1])
         self.ops.append(dict(kind=OP_FUSE, out_slot=out, relu=int(relu), fuse_in=[t for t, _ in ins],
-                             fuse_shift=[s for _, s in ins]))
+                             fuse_shift=[s for _, s in ins], lane=self.lane))
         return out
 
     def pool(self, x):
-        self.ops.append(dict(kind=OP_POOL, in_slot=x))
+        self.ops.append(dict(kind=OP_POOL, in_slot=x, lane=self.lane))
 
     def finalize(self):
         """Liveness-based slot reuse.  Returns (ops with physical slots, slots, virtual->physical map)."""
@@ -204,7 +211,9 @@ class _Graph:
             o = dict(o)
             if 'out_slot' in o and o['out_slot'] not in phys:
                 t = self.tensors[o['out_slot']]
-                key = (t['channels'], t['div'])
+                # slots are only recycled within a lane: a recycled slot orders its new writer after the old readers
+                # (WAR), which across lanes would serialise branches that are independent
+                key = (t['channels'], t['div'], t['lane'])
                 # never alias an op's output with one of its own inputs
                 busy = {phys[r] for r in reads(o) if r in phys}
                 cand = [s for s in free.get(key, []) if s not in busy]
@@ -212,7 +221,7 @@ class _Graph:
                     s = cand[0]
                     free[key].remove(s)
                 else:
-                    slots.append(dict(t))
+                    slots.append(dict(channels=t['channels'], div=t['div']))
                     s = len(slots) - 1
                 phys[o['out_slot']] = s
             for k in ('in_slot', 'res_slot', 'out_slot'):
@@ -224,7 +233,7 @@ class _Graph:
             for t in set(reads(self.ops[i]) + ([self.ops[i]['out_slot']] if 'out_slot' in self.ops[i] else [])):
                 if last.get(t) == i and t not in self.keep and t in phys:
                     tt = self.tensors[t]
-                    free.setdefault((tt['channels'], tt['div']), []).append(phys[t])
+                    free.setdefault((tt['channels'], tt['div'], tt['lane']), []).append(phys[t])
         return out_ops, slots, phys
 
 
@@ -404,41 +413,66 @@ class HighResolutionNet(nn.Module):
     # ------------------------------------------------------------------ compilation to the op program
     def _block_ops(self, g, blk, x):
         if isinstance(blk, BasicBlock):
+            if blk.downsample is not None:
+                raise ValueError('shapy_b200: BasicBlock with a downsample branch is not on the SHAPY_A path '
+                                 '(network_defaults.py:92-132 never creates one)')
             t = g.conv(blk.conv1, blk.bn1, x, relu=True)
             return g.conv(blk.conv2, blk.bn2, t, relu=True, res=x)
         idt = x
         if blk.downsample is not None:
+            lane = g.lane
+            g.on(lane + 1)                                 # independent of conv1 / conv2: runs beside them
             if isinstance(blk.downsample, nn.Conv2d):      # conv_layers: bare 1x1 conv, no BN (hrnet.py:361-373)
                 idt = g.conv(blk.downsample, None, x, relu=False)
             else:
                 idt = g.conv(blk.downsample[0], blk.downsample[1], x, relu=False)
+            g.on(lane)
         t = g.conv(blk.conv1, blk.bn1, x, relu=True)
         t = g.conv(blk.conv2, blk.bn2, t, relu=True)
         return g.conv(blk.conv3, blk.bn3, t, relu=True, res=idt)
 
     def _module_ops(self, g, mod, xs):
+        # branch i runs in lane i: the branches of a module are independent (reference hrnet.py:175-181)
         xs = list(xs)
         for i in range(mod.num_branches):
+            g.on(i)
             for blk in mod.branches[i]:
                 xs[i] = self._block_ops(g, blk, xs[i])
         if mod.num_branches == 1:
+            g.on(0)
             return xs
-        outs = []
-        for i in range(len(mod.fuse_layers)):
-            terms = []
+        # fuse stage: the (i, j) conv chains are independent of each other (hrnet.py:184-191); they are dealt to the lanes
+        # longest first onto the least loaded lane (cost ~ MACs + a fixed launch term), the sum of output i runs in lane i
+        nout = len(mod.fuse_layers)
+        terms = [[None] * mod.num_branches for _ in range(nout)]
+        chains = []
+        for i in range(nout):
             for j in range(mod.num_branches):
                 if j == i:
-                    terms.append((xs[j], 0))
-                elif j > i:
-                    fl = mod.fuse_layers[i][j]
-                    terms.append((g.conv(fl[0], fl[1], xs[j], relu=False), j - i))
-                else:
-                    t = xs[j]
-                    chain = mod.fuse_layers[i][j]
-                    for k, seq in enumerate(chain):
-                        t = g.conv(seq[0], seq[1], t, relu=(k != len(chain) - 1))
-                    terms.append((t, 0))
-            outs.append(g.fuse(terms, relu=True))
+                    terms[i][j] = (xs[j], 0)
+                    continue
+                fl = mod.fuse_layers[i][j]
+                seqs = [fl] if j > i else list(fl)
+                cost, div = 0.0, g.tensors[xs[j]]['div']
+                for seq in seqs:
+                    c = seq[0]
+                    div *= c.stride[0]
+                    cost += c.in_channels * c.out_channels * c.kernel_size[0] ** 2 / float(div * div) + 2e3
+                chains.append((cost, i, j, seqs))
+        load = [0.0] * N_LANES
+        for cost, i, j, seqs in sorted(chains, key=lambda c: -c[0]):
+            lane = min(range(N_LANES), key=lambda l: load[l])
+            load[lane] += cost
+            g.on(lane)
+            t = xs[j]
+            for k, seq in enumerate(seqs):
+                t = g.conv(seq[0], seq[1], t, relu=(j < i and k != len(seqs) - 1))
+            terms[i][j] = (t, j - i if j > i else 0)
+        outs = []
+        for i in range(nout):
+            g.on(i)
+            outs.append(g.fuse(terms[i], relu=True))
+        g.on(0)
         return outs
 
     def build_program(self):
@@ -452,6 +486,7 @@ class HighResolutionNet(nn.Module):
         def transition(layers, ys, nprev):
             xs = []
             for i, tl in enumerate(layers):
+                g.on(i)
                 if tl is None:
                     xs.append(ys[i])
                 else:
@@ -463,6 +498,7 @@ class HighResolutionNet(nn.Module):
                         for seq in tl:
                             t = g.conv(seq[0], seq[1], t, relu=True)
                         xs.append(t)
+            g.on(0)
             return xs
         ys = transition(self.transition1, [x], 1)
         for mod in self.stage2:
@@ -484,11 +520,16 @@ class HighResolutionNet(nn.Module):
                 t = g.conv(seq[3 * i], seq[3 * i + 1], t, relu=True, out=cat if last else None,
                            out_coff=coff if last else 0)
             return t
+        g.on(0)
         subsample(self.subsample_4, ys[0], 0)
+        g.on(1)
         subsample(self.subsample_3, ys[1], 384)
+        g.on(2)
         subsample(self.subsample_2, ys[2], 768)
         # x1 = y_list[3] is concatenated as is: copy through a 1-input fuse (no ReLU) into the slice
-        g.ops.append(dict(kind=OP_FUSE, out_slot=cat, out_coff=1152, relu=0, fuse_in=[ys[3]], fuse_shift=[0]))
+        g.on(3)
+        g.ops.append(dict(kind=OP_FUSE, out_slot=cat, out_coff=1152, relu=0, fuse_in=[ys[3]], fuse_shift=[0], lane=g.lane))
+        g.on(0)
         f = cat
         for blk in self.conv_layers:
             f = self._block_ops(g, blk, f)

@@ -287,6 +287,7 @@ class HrnetPlan:
             od[i].kind, od[i].conv = o['kind'], o.get('conv', -1)
             od[i].in_slot, od[i].out_slot, od[i].out_coff = o.get('in_slot', -1), o.get('out_slot', -1), o.get('out_coff', 0)
             od[i].res_slot, od[i].relu = o.get('res_slot', -1), int(o.get('relu', 0))
+            od[i].lane = int(o.get('lane', 0))
             ins = o.get('fuse_in', [])
             od[i].n_in = len(ins)
             for k, (s, sh) in enumerate(zip(ins, o.get('fuse_shift', []))):

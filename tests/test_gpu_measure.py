@@ -146,3 +146,27 @@ def test_mmi_op_random_meshes(data, Q, F, M):
             n_hits += len(f1)
     if F >= 500:
         assert n_hits > 0
+
+
+def test_config4_4096_random_beta_bodies_vs_oracle(data):
+    """BASELINE configs[3]: 4 096 clipped-normal betas (seed 3) -> T-pose bodies -> measurements in one launch each;
+    64 of the 4 096 rows against the CPU oracle (shape blend restated in numpy, measure_oracle)."""
+    g, lm, ops = data
+    smplx = synth.make_smplx()
+    packed = ops.SmplxModel(dict(smplx), 'cuda')
+    betas = torch.randn(4096, 10, generator=torch.Generator().manual_seed(3)).clamp(-3, 3)
+    vs = ops.smplx_forward_shape(packed, betas.cuda())
+    faces = smplx['faces_tensor'].to(torch.int32).cuda()
+    out, _, _, status = ops.measure(ops.make_landmarks(lm), v_shaped=vs, faces_i32=faces, return_points=True)
+    assert int(status.item()) == 0
+    out = out.cpu().numpy()
+    rows = np.random.default_rng(5).choice(4096, 64, replace=False)
+    vt = smplx['v_template'].double().numpy()
+    S = smplx['shapedirs'].double().numpy()                                    # (V, 3, 10)
+    f = smplx['faces_tensor'].numpy()
+    for r in rows:
+        ref_v = (vt + S @ betas[r].double().numpy()).astype(np.float32)
+        assert np.abs(vs[r].cpu().numpy() - ref_v).max() < 2e-6
+        ref = measure_oracle.measure(ref_v, f, lm)
+        for i, name in enumerate(('mass', 'height', 'chest', 'waist', 'hips')):
+            assert abs(out[r, i] - ref[name]) / abs(ref[name]) < 1e-4, (int(r), name, out[r, i], ref[name])
