@@ -38,7 +38,10 @@ class BodyMeasurements(nn.Module):
         self.register_buffer('chest_bcs', torch.tensor(lm['chest']['bc'], dtype=torch.float32))
         self.register_buffer('belly_bcs', torch.tensor(lm['waist']['bc'], dtype=torch.float32))
         self.register_buffer('hips_bcs', torch.tensor(lm['hips']['bc'], dtype=torch.float32))
+        # accepted for config compatibility; the fused kernel has its own fixed capacity (1024 points per plane,
+        # 4x the reference default) and reports overflow through NaN + `last_status` instead of truncating
         self.max_collisions = cfg.get('max_collisions', 256)
+        self.last_status = None
         self._lm = None
 
     def extra_repr(self):
@@ -62,10 +65,18 @@ class BodyMeasurements(nn.Module):
         self._lm = None
         return super()._load_from_state_dict(*args, **kwargs)
 
-    @staticmethod
-    def _pack(out):
+    def _pack(self, out):
         names = ('mass', 'height', 'chest', 'waist', 'hips')
+        # device status word of the launch (non-zero: some body overflowed the kernel's fixed point capacity and its
+        # circumferences are NaN); kept for callers that want to check it at their next synchronisation point
+        self.last_status = getattr(out, 'status', None)
         return {'measurements': {n: {'tensor': out[:, i]} for i, n in enumerate(names)}}
+
+    def check_status(self):
+        """Raises if the last launch overflowed the kernel's point buffers (one host synchronisation)."""
+        st = getattr(self, 'last_status', None)
+        if st is not None and int(st.item()) != 0:
+            raise RuntimeError('BodyMeasurements: intersection-point capacity exceeded; affected values are NaN')
 
     def forward_vertices(self, v_shaped, faces_i32):
         """Fast path: (B, V, 3) vertices + (F, 3) int32 faces; no (B, F, 3, 3) tensor is materialised."""

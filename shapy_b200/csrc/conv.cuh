@@ -51,9 +51,11 @@ __device__ __forceinline__ void split_store(float v, __half &hi, __half &lo) {
 // ---- engines (each returns SHAPY_OK or an error code; all launches on `st`)
 int launch_conv_simt(const ConvW &w, const ActView &in, const ActView &out, const ActView *res, bool relu,
                      cudaStream_t st);
-int launch_stem(const ConvW &w, const float *images, int N, int H, int W, const ActView &out, cudaStream_t st);
+int launch_stem(const ConvW &w, const float *images, const float *const *images_cell, int N, int H, int W,
+                const ActView &out, cudaStream_t st);
 int launch_fuse(const ActView *ins, const int *shifts, int n_in, const ActView &out, bool relu, cudaStream_t st);
-int launch_pool(const ActView &in, float *feats, cudaStream_t st);
+int launch_pool(const ActView &in, float *feats, float *const *feats_cell, cudaStream_t st);
+int launch_set_io_cells(void **cells, const float *images, float *feats, cudaStream_t st);   // cells[0] = images, [1] = feats
 int launch_nhwc_split(const float *x, const ActView &out, cudaStream_t st);          // fp32 NHWC -> planes
 int launch_nhwc_merge(const ActView &in, float *y, bool to_nchw, cudaStream_t st);   // planes -> fp32
 

@@ -128,9 +128,12 @@ int launch_conv_simt(const ConvW &w, const ActView &in, const ActView &out, cons
 
 // ---------------------------------------------------------------------------------------------
 // Stem: 3x3 stride-2 conv on the fp32 NCHW network input (hrnet.py:209-211), BN + ReLU folded.
-__global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img, int N, int H, int W,
+// `cell` (optional): device cell holding the image pointer, read at run time, so that a captured CUDA graph of the
+// network can be replayed on any input buffer (hrnet.cu); null = use `img`.
+__global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img_direct, const float *const *cell, int N, int H, int W,
                                                    const float *__restrict__ wf, const float *__restrict__ bias, int Cout,
                                                    __half *out_hi, __half *out_lo, int ctot, int coff) {
+  const float *__restrict__ img = cell ? *cell : img_direct;
   // one thread = one output pixel x 16 output channels; the 4 (Cout = 64) threads of a pixel are adjacent lanes, so a
   // warp writes 8 pixels x 128 contiguous bytes per plane and reads its weights as 4 distinct broadcast LDS.128.
   extern __shared__ __align__(16) float ws[];  // [27][Cout] + bias[Cout]
@@ -180,9 +183,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const float *__restrict__ img
 // Same convolution, 4 consecutive output pixels x 16 output channels per thread: every weight vector read from shared
 // memory feeds 4 pixels (1 LDS.128 per 16 FMAs instead of per 4; the one-pixel variant above is LDS-bound at ~355 us
 // for 64 x 224 x 224), and the 9 input columns of a row are two aligned LDG.128 plus one scalar.
-__global__ void __launch_bounds__(256, 2) stem4_kernel(const float *__restrict__ img, int N, int H, int W,
+__global__ void __launch_bounds__(256, 2) stem4_kernel(const float *__restrict__ img_direct, const float *const *cell, int N, int H, int W,
                                                     const float *__restrict__ wf, const float *__restrict__ bias, int Cout,
                                                     __half *out_hi, __half *out_lo, int ctot, int coff) {
+  const float *__restrict__ img = cell ? *cell : img_direct;
   extern __shared__ __align__(16) float ws[];  // [27][Cout] + bias[Cout]
   for (int i = threadIdx.x; i < 27 * Cout + Cout; i += blockDim.x) ws[i] = i < 27 * Cout ? wf[i] : bias[i - 27 * Cout];
   __syncthreads();
@@ -237,21 +241,24 @@ __global__ void __launch_bounds__(256, 2) stem4_kernel(const float *__restrict__
   }
 }
 
-int launch_stem(const ConvW &w, const float *images, int N, int H, int W, const ActView &out, cudaStream_t st) {
+// images_cell != null: the kernels read the image pointer from that device cell (`images` is then only used for the
+// alignment decision and may be any pointer with the alignment the cell's future contents will have)
+int launch_stem(const ConvW &w, const float *images, const float *const *images_cell, int N, int H, int W, const ActView &out,
+                cudaStream_t st) {
   SHAPY_REQUIRE(w.cin == 3 && w.ksize == 3 && w.stride == 2 && w.cout % 16 == 0 && w.w_f32, "stem: unsupported conv");
   SHAPY_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: odd input size");
   size_t smem = (size_t)(27 * w.cout + w.cout) * sizeof(float);
   if (W % 8 == 0 && ((uintptr_t)images & 15) == 0 && out.Ctot % 16 == 0 && out.coff % 16 == 0 &&
       ((uintptr_t)out.hi & 31) == 0 && (!out.lo || ((uintptr_t)out.lo & 31) == 0)) {
     long long total4 = (long long)N * (H / 2) * (W / 8) * (w.cout / 16);
-    stem4_kernel<<<(unsigned)((total4 + 255) / 256), 256, smem, st>>>(images, N, H, W, w.w_f32, w.bias, w.cout, out.hi,
-                                                                      out.lo, out.Ctot, out.coff);
+    stem4_kernel<<<(unsigned)((total4 + 255) / 256), 256, smem, st>>>(images, images_cell, N, H, W, w.w_f32, w.bias, w.cout,
+                                                                      out.hi, out.lo, out.Ctot, out.coff);
     SHAPY_LAUNCH_CHECK();
     return SHAPY_OK;
   }
   long long total = (long long)N * (H / 2) * (W / 2) * (w.cout / 16);
-  stem_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(images, N, H, W, w.w_f32, w.bias, w.cout, out.hi,
-                                                                  out.lo, out.Ctot, out.coff);
+  stem_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(images, images_cell, N, H, W, w.w_f32, w.bias, w.cout,
+                                                                  out.hi, out.lo, out.Ctot, out.coff);
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;
 }
@@ -354,7 +361,9 @@ int launch_fuse(const ActView *ins, const int *shifts, int n_in, const ActView &
 
 // ---------------------------------------------------------------------------------------------
 // xf.mean(dim=(2,3))  (hrnet.py:484): one thread per (image, channel).
-__global__ void pool_kernel(const __half *hi, const __half *lo, int N, int HW, int C, int ctot, int coff, float *feats) {
+__global__ void pool_kernel(const __half *hi, const __half *lo, int N, int HW, int C, int ctot, int coff, float *feats_direct,
+                            float *const *cell) {
+  float *feats = cell ? *cell : feats_direct;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   int n = i / C, c = i % C;
@@ -366,9 +375,21 @@ __global__ void pool_kernel(const __half *hi, const __half *lo, int N, int HW, i
   feats[i] = s / (float)HW;
 }
 
-int launch_pool(const ActView &in, float *feats, cudaStream_t st) {
+int launch_pool(const ActView &in, float *feats, float *const *feats_cell, cudaStream_t st) {
   int total = in.N * in.C;
-  pool_kernel<<<ceil_div(total, 128), 128, 0, st>>>(in.hi, in.lo, in.N, in.H * in.W, in.C, in.Ctot, in.coff, feats);
+  pool_kernel<<<ceil_div(total, 128), 128, 0, st>>>(in.hi, in.lo, in.N, in.H * in.W, in.C, in.Ctot, in.coff, feats, feats_cell);
+  SHAPY_LAUNCH_CHECK();
+  return SHAPY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void set_io_cells_kernel(const void **cells, const void *images, void *feats) {
+  cells[0] = images;
+  cells[1] = feats;
+}
+
+int launch_set_io_cells(void **cells, const float *images, float *feats, cudaStream_t st) {
+  set_io_cells_kernel<<<1, 1, 0, st>>>((const void **)cells, images, feats);
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;
 }

@@ -35,9 +35,18 @@ struct shapy_hrnet {
   std::vector<cudaEvent_t> op_ev;            // per op: recorded after the op when an op of another lane waits on it
   std::vector<std::vector<int>> op_waits;    // per op: ops of other lanes to wait for (transitively reduced)
   std::vector<char> op_pdl;                  // per op: programmatic dependent launch allowed (no other lane can be running)
+  // CUDA graph of one forward (captured on the second forward after a bind, replayed afterwards): the stem and the
+  // pool read the image / feature pointers from `io_cells`, so one graph serves any input and output buffer
+  void **io_cells = nullptr;                 // device: [0] = images, [1] = feats
+  cudaStream_t cap_stream = nullptr;         // capture origin (the caller's stream may be the legacy default stream)
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_kernels = 0;
+  bool warm = false, graph_failed = false;
 };
 
 static void free_plans(shapy_hrnet *p) {
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  p->graph_exec = nullptr; p->graph_kernels = 0; p->warm = false; p->graph_failed = false;
   for (auto *u : p->plans) if (u) umma_plan_destroy(u);
   p->plans.clear();
   for (auto e : p->op_ev) if (e) cudaEventDestroy(e);
@@ -54,6 +63,10 @@ static void free_lanes(shapy_hrnet *p) {
   }
   if (p->fork_ev) cudaEventDestroy(p->fork_ev);
   p->fork_ev = nullptr;
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  p->cap_stream = nullptr;
+  if (p->io_cells) cudaFree(p->io_cells);
+  p->io_cells = nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -97,11 +110,12 @@ static int max_lanes() {
   if (v < 0) { const char *e = getenv("SHAPY_HRNET_LANES"); v = e ? std::max(1, std::min(atoi(e), (int)SHAPY_MAX_LANES)) : SHAPY_MAX_LANES; }
   return v;
 }
-// SHAPY_PDL: 0 never, 1 every conv launch, 2 (default) only where no other lane can be running: a dependent kernel
-// launched early occupies an SM while it waits, which would keep another lane's kernel from back-filling that SM
+// SHAPY_PDL: 0 never, 1 (default) every conv launch, 2 only where no other lane can be running.  Measured (B = 64,
+// profiles/r02_lanes_ab.txt): 4 lanes with PDL everywhere 9.70 ms, with policy 2 10.43 ms, 1 lane 10.80 ms -- the
+// early-launched dependent's prologue overlap is worth more than the SMs it holds while it waits.
 static int pdl_policy() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("SHAPY_PDL"); v = e ? atoi(e) : 2; }
+  if (v < 0) { const char *e = getenv("SHAPY_PDL"); v = e ? atoi(e) : 1; }
   return v;
 }
 
@@ -313,15 +327,29 @@ static int bind(shapy_hrnet *p, void *ws, int B, int H, int W) {
   return SHAPY_OK;
 }
 
-extern "C" int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int B, int H, int W, float *feats,
-                                   void *workspace, size_t workspace_bytes, void *stream) {
-  SHAPY_REQUIRE(p && images && feats && workspace, "shapy_hrnet_forward: null argument");
-  SHAPY_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "shapy_hrnet_forward: image size %dx%d must be a multiple of 32", H, W);
-  SHAPY_REQUIRE(workspace_bytes >= shapy_hrnet_workspace_bytes(p, B, H, W), "shapy_hrnet_forward: workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (p->ws != workspace || p->B != B || p->H != H || p->W != W) {
-    int rc = bind(p, workspace, B, H, W);
-    if (rc) return rc;
+// Enqueues one forward on `st` (+ the lane streams).  cells != null: the stem / pool read their buffers from the device
+// cells (graph capture); `images` then only conveys the alignment of the future inputs.
+// SHAPY_HRNET_TRACE=<file>: the direct path records a start / end event pair around every op on its lane stream and
+// shapy_hrnet_forward() dumps "op lane kind cin cout k s div start_us end_us" per op after a device synchronise
+// (a debugging aid: the events add a little serialisation; never active under graph capture).
+struct TraceEv { cudaEvent_t a, b; };
+static std::vector<TraceEv> g_trace;
+static cudaEvent_t g_trace0 = nullptr;
+static const char *trace_path() {
+  static const char *v = getenv("SHAPY_HRNET_TRACE");
+  return v;
+}
+
+static int enqueue_forward(shapy_hrnet *p, const float *images, float *feats, void **cells, int B, int H, int W,
+                           cudaStream_t st) {
+  const bool trace = trace_path() && !cells;
+  if (trace) {
+    if (g_trace.size() != p->ops.size()) {
+      g_trace.resize(p->ops.size());
+      for (auto &t : g_trace) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+      cudaEventCreate(&g_trace0);
+    }
+    cudaEventRecord(g_trace0, st);
   }
   // fork: the other lanes start after everything already queued on the caller's stream (the input images, and the
   // join of the previous forward on this workspace)
@@ -334,11 +362,13 @@ extern "C" int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int B,
     const shapy_op_t &o = p->ops[i];
     cudaStream_t ls = p->lane_stream[lane_of(o)];
     for (int j : p->op_waits[i]) SHAPY_CUDA_TRY(cudaStreamWaitEvent(ls, p->op_ev[j], 0));
+    if (trace) cudaEventRecord(g_trace[i].a, ls);
     int rc = SHAPY_OK;
     switch (o.kind) {
       case SHAPY_OP_STEM: {
         const ConvW &w = p->convs[o.conv];
-        rc = launch_stem(w, images, B, H, W, view_of(p, o.out_slot, o.out_coff, w.cout), ls);
+        rc = launch_stem(w, images, cells ? (const float *const *)&cells[0] : nullptr, B, H, W,
+                         view_of(p, o.out_slot, o.out_coff, w.cout), ls);
         break;
       }
       case SHAPY_OP_CONV: {
@@ -360,13 +390,14 @@ extern "C" int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int B,
         break;
       }
       case SHAPY_OP_POOL:
-        rc = launch_pool(p->views[o.in_slot], feats, ls);
+        rc = launch_pool(p->views[o.in_slot], feats, cells ? (float *const *)&cells[1] : nullptr, ls);
         break;
       default:
         set_error("unknown op kind %d", o.kind);
         rc = SHAPY_ERR_ARG;
     }
     if (rc) return rc;
+    if (trace) cudaEventRecord(g_trace[i].b, ls);
     if (p->op_ev[i]) SHAPY_CUDA_TRY(cudaEventRecord(p->op_ev[i], ls));
   }
   // join: the caller's stream continues after every lane has drained
@@ -374,6 +405,89 @@ extern "C" int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int B,
     SHAPY_CUDA_TRY(cudaEventRecord(p->join_ev[l], p->lane_stream[l]));
     SHAPY_CUDA_TRY(cudaStreamWaitEvent(st, p->join_ev[l], 0));
   }
+  return SHAPY_OK;
+}
+
+static bool graph_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SHAPY_HRNET_GRAPH");
+    v = (e && e[0] == '0') || getenv("SHAPY_CONV_PHASES") ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Captures one forward (all lanes) into a CUDA graph.  Returns false (and leaves the direct path in charge) on any
+// failure; never leaves a stream in capture mode.
+static bool capture_graph(shapy_hrnet *p, const float *images, int B, int H, int W) {
+  if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+  if (!p->io_cells && cudaMalloc((void **)&p->io_cells, 2 * sizeof(void *)) != cudaSuccess) return false;
+  if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+  const long long n0 = shapy_launch_count();
+  const int rc = enqueue_forward(p, images, nullptr, p->io_cells, B, H, W, p->cap_stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
+  const long long n = shapy_launch_count() - n0;
+  count_launch((int)-n);                      // nothing ran during the capture
+  if (rc || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return false;
+  }
+  cudaGraphExec_t ex = nullptr;
+  const cudaError_t e2 = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (e2 != cudaSuccess) { cudaGetLastError(); return false; }
+  p->graph_exec = ex;
+  p->graph_kernels = n;
+  if (getenv("SHAPY_CONV_DEBUG")) fprintf(stderr, "[hrnet] captured a CUDA graph with %lld kernel nodes\n", n);
+  return true;
+}
+
+extern "C" int shapy_hrnet_forward(shapy_hrnet_t *p, const float *images, int B, int H, int W, float *feats,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+  SHAPY_REQUIRE(p && images && feats && workspace, "shapy_hrnet_forward: null argument");
+  SHAPY_REQUIRE(B > 0 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "shapy_hrnet_forward: image size %dx%d must be a multiple of 32", H, W);
+  SHAPY_REQUIRE(workspace_bytes >= shapy_hrnet_workspace_bytes(p, B, H, W), "shapy_hrnet_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->ws != workspace || p->B != B || p->H != H || p->W != W) {
+    int rc = bind(p, workspace, B, H, W);
+    if (rc) return rc;
+  }
+  // CUDA graph replay: from the second forward of a binding on, unless the caller is itself capturing (then the direct
+  // launches below simply become part of the caller's graph) or the input is not 16-byte aligned (the captured stem
+  // kernel uses 128-bit loads)
+  bool use_graph = graph_enabled() && !trace_path() && p->warm && !p->graph_failed && ((uintptr_t)images & 15) == 0;
+  if (use_graph) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); use_graph = false; }
+  }
+  if (use_graph && !p->graph_exec && !capture_graph(p, images, B, H, W)) { p->graph_failed = true; use_graph = false; }
+  if (!use_graph) {
+    int rc = enqueue_forward(p, images, feats, nullptr, B, H, W, st);
+    p->warm = true;
+    if (!rc && trace_path()) {
+      cudaDeviceSynchronize();
+      if (FILE *f = fopen(trace_path(), "w")) {
+        for (size_t i = 0; i < p->ops.size(); ++i) {
+          const shapy_op_t &o = p->ops[i];
+          float t0 = 0, t1 = 0;
+          cudaEventElapsedTime(&t0, g_trace0, g_trace[i].a);
+          cudaEventElapsedTime(&t1, g_trace0, g_trace[i].b);
+          const ConvW *w = (o.kind == SHAPY_OP_CONV || o.kind == SHAPY_OP_STEM) ? &p->convs[o.conv] : nullptr;
+          fprintf(f, "%zu %d %d %d %d %d %d %d %.2f %.2f\n", i, lane_of(o), o.kind, w ? w->cin : 0, w ? w->cout : 0,
+                  w ? w->ksize : 0, w ? w->stride : 0, p->slots[o.kind == SHAPY_OP_POOL ? o.in_slot : o.out_slot].div,
+                  t0 * 1e3, t1 * 1e3);
+        }
+        fclose(f);
+      }
+    }
+    return rc;
+  }
+  int rc = launch_set_io_cells(p->io_cells, images, feats, st);
+  if (rc) return rc;
+  SHAPY_CUDA_TRY(cudaGraphLaunch(p->graph_exec, st));
+  count_launch((int)p->graph_kernels);
   return SHAPY_OK;
 }
 

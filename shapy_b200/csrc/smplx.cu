@@ -19,44 +19,14 @@
 #include <cmath>
 #include <cstring>
 
-#include "common.cuh"
+#include "smplx.cuh"
+#include "umma.cuh"
 
 namespace shapy {
 
-constexpr int kMaxJoints = 64;
-constexpr int kMaxCoef = 32;
 constexpr int TV = 32;  // vertices per tile (one per lane)
 constexpr int TB = 32;  // bodies per tile (8 per warp, 4 warps)
 constexpr int KC = 32;  // pose-feature rows staged per chunk
-
-struct SmplxDev {
-  int V, J, NB, NE, NC, F, L, D, rows, K, n_chain, n_levels, ell_w_n, n_extra, n_over;
-  float *v_template, *shapedirs /* [NC][3V] */, *posedirs /* [(J-1)*9][3V] */;
-  float *basis;   /* [NC + (J-1)*9][V3p]: shape, expression and pose blend-shape rows, 16-byte aligned rows */
-  int V3p;
-  float *J_template /* [3J] */, *J_dirs /* [3J][NC] */;
-  int *ell_idx;   /* [W][V] */
-  float *ell_w;   /* [W][V] */
-  int *parents, *level_joints, *level_off; /* level_off[n_levels+1] */
-  int *faces;     /* [F][3] */
-  int *lmk_vidx;  /* [L][3] */
-  float *lmk_bc;  /* [L][3] */
-  int *dyn_vidx;  /* [rows][D][3] */
-  float *dyn_bc;  /* [rows][D][3] */
-  int *neck;      /* [n_chain] */
-  int *ex_ptr, *ex_col;
-  float *ex_val;
-  int *over_src, *over_tgt;
-};
-
-}  // namespace shapy
-
-struct shapy_smplx {
-  shapy::SmplxDev d;
-  std::vector<void *> allocs;
-};
-
-namespace shapy {
 
 // ----------------------------------------------------------------------------------------------
 __global__ void decode_rot6d_kernel(const float *__restrict__ raw, int n, float *__restrict__ rot) {
@@ -301,6 +271,9 @@ struct JointsArgs {
 };
 
 __global__ void __launch_bounds__(128) smplx_joints_kernel(JointsArgs a) {
+  // launched as a programmatic dependent of the kernel that writes the vertices: its launch latency overlaps that
+  // kernel's tail; everything below reads the predecessor's output, so wait for its completion first
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const SmplxDev &m = a.m;
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   extern __shared__ float sm[];
@@ -557,6 +530,40 @@ extern "C" int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t 
   for (int i = 0; i < s.n_over; ++i) { os[i] = (int)d->source_idxs[i]; ot[i] = (int)d->target_idxs[i]; }
   s.over_src = upload(m, os, err);
   s.over_tgt = upload(m, ot, err);
+  {
+    // ---- operands of the fused tcgen05 LBS kernel (smplx_lbs.cu)
+    const int Vpad = (V + 127) / 128 * 128, KP = (J - 1) * 9, KPpad = (KP + 63) / 64 * 64;
+    s.Vpad = Vpad; s.KPpad = KPpad;
+    std::vector<__half> bh((size_t)3 * Vpad * KPpad, __float2half_rn(0.f)), bl(bh.size(), __float2half_rn(0.f));
+    for (int k = 0; k < KP; ++k) {
+      const float *row = d->posedirs + (size_t)k * V * 3;
+      for (int v = 0; v < V; ++v)
+        for (int c = 0; c < 3; ++c) {
+          const float x = row[(size_t)v * 3 + c] * kPoseScale;
+          const __half h = __float2half_rn(x);
+          const size_t o = ((size_t)c * Vpad + v) * KPpad + k;
+          bh[o] = h;
+          bl[o] = __float2half_rn((x - __half2float(h)) * 2048.0f);
+        }
+    }
+    s.pbasis_hi = upload(m, bh, err);
+    s.pbasis_lo = upload(m, bl, err);
+    std::vector<float> sp((size_t)(NB + 1) * 3 * Vpad, 0.f);
+    for (int v = 0; v < V; ++v)
+      for (int c = 0; c < 3; ++c) {
+        for (int l = 0; l < NB; ++l) sp[(size_t)(l * 3 + c) * Vpad + v] = d->shapedirs[((size_t)v * 3 + c) * NB + l];
+        sp[(size_t)(NB * 3 + c) * Vpad + v] = d->v_template[(size_t)v * 3 + c];
+      }
+    s.shape_planes = upload(m, sp, err);
+    m->fused_ok = false;
+    if (err == cudaSuccess && get_encode()) {
+      cuuint64_t dims[3] = {(cuuint64_t)KPpad, (cuuint64_t)Vpad, 3};
+      cuuint64_t strides[2] = {(cuuint64_t)KPpad * 2, (cuuint64_t)Vpad * KPpad * 2};
+      cuuint32_t box[3] = {32, 128, 3};
+      m->fused_ok = encode(&m->basis_map_hi, s.pbasis_hi, 3, dims, strides, box, 32) &&
+                    encode(&m->basis_map_lo, s.pbasis_lo, 3, dims, strides, box, 32);
+    }
+  }
   if (err != cudaSuccess) {
     set_error("shapy_smplx_create: %s", cudaGetErrorString(err));
     shapy_smplx_destroy(m);
@@ -612,20 +619,41 @@ extern "C" int shapy_smplx_forward(const shapy_smplx_t *m, const float *betas, c
   int *lut = (int *)w; w += align_up((size_t)B * sizeof(int), 256);
   float *jscratch = (float *)w;
   const int Kp = (n_rot - 1) * 9;
-  PoseArgs pa{d, betas, d.NE ? expr : nullptr, rot, n_rot, B, bpad(B), Kp, A, pfT, joints ? joints : jscratch, lut};
-  smplx_pose_kernel<<<B, 128, 0, st>>>(pa);
-  SHAPY_LAUNCH_CHECK();
-  if (vertices || v_shaped) {
-    VertexArgs va{d, betas, d.NE ? expr : nullptr, A, pfT, B, bpad(B), Kp, vertices, v_shaped};
-    dim3 grid(ceil_div(d.V, TV), ceil_div(B, TB));
-    smplx_vertex_kernel<<<grid, 128, 0, st>>>(va);
+  // fused tcgen05 kernel (pose chain + shape + pose blend + skinning in one launch) when the configuration allows:
+  // no expression coefficients, posed vertices requested, 10 betas, n_rot <= 29
+  bool fused = false;
+  if (vertices && !(d.NE && expr)) {
+    const int rc = launch_lbs_fused(m, betas, rot, n_rot, B, vertices, v_shaped, joints ? joints : jscratch, lut, st);
+    if (rc == SHAPY_OK) fused = true;
+    else if (rc != SHAPY_ERR_UNSUPPORTED) return rc;
+  }
+  if (!fused) {
+    PoseArgs pa{d, betas, d.NE ? expr : nullptr, rot, n_rot, B, bpad(B), Kp, A, pfT, joints ? joints : jscratch, lut};
+    smplx_pose_kernel<<<B, 128, 0, st>>>(pa);
     SHAPY_LAUNCH_CHECK();
+    if (vertices || v_shaped) {
+      VertexArgs va{d, betas, d.NE ? expr : nullptr, A, pfT, B, bpad(B), Kp, vertices, v_shaped};
+      dim3 grid(ceil_div(d.V, TV), ceil_div(B, TB));
+      smplx_vertex_kernel<<<grid, 128, 0, st>>>(va);
+      SHAPY_LAUNCH_CHECK();
+    }
   }
   if (joints && (d.L + d.D + d.n_extra > 0 || proj_joints)) {
     JointsArgs ja{d, vertices, camera, lut, B, joints, proj_joints};
     size_t smem = ((size_t)d.K * 3 + (size_t)std::max(d.n_extra, 1) * 3) * sizeof(float);
-    smplx_joints_kernel<<<B, 128, smem, st>>>(ja);
-    SHAPY_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(B);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_joints_kernel, ja));
+    count_launch();
   }
   return SHAPY_OK;
 }

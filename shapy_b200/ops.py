@@ -166,8 +166,13 @@ def make_landmarks(lm: dict) -> _lib.MeasureLandmarks:
 
 
 def measure(landmarks: _lib.MeasureLandmarks, v_shaped=None, faces_i32=None, triangles=None, return_points=False,
-            max_points=512):
-    """Returns (B, 5) = mass, height, chest, waist, hips.  Either (v_shaped, faces_i32) or triangles (B,F,3,3)."""
+            max_points=1024, strict=False):
+    """Returns (B, 5) = mass, height, chest, waist, hips.  Either (v_shaped, faces_i32) or triangles (B,F,3,3).
+
+    The kernel's point / candidate buffers have a fixed capacity (1024 points per plane; the reference's
+    `max_collisions` has no equivalent).  A body that overflows them gets NaN circumferences, never a truncated value,
+    and the device status word is set: it is returned as `out.status` (a 1-element int32 CUDA tensor, readable at the
+    caller's next synchronisation point) and `strict=True` checks it here (one host synchronisation) and raises."""
     if triangles is not None:
         x = _cuda_f32(triangles, 'triangles')
         B, F = x.shape[0], x.shape[1]
@@ -192,6 +197,10 @@ def measure(landmarks: _lib.MeasureLandmarks, v_shaped=None, faces_i32=None, tri
         else:
             check(lib().shapy_measure_forward(ptr(x), ptr(faces_i32), B, V, F, C.byref(landmarks), ptr(out), ptr(pts),
                                               ptr(cnt), max_points, ptr(status), stream_ptr()), 'measure')
+    out.status = status
+    if strict and int(status.item()) != 0:
+        raise RuntimeError('shapy_b200 measure: a slicing plane produced more intersection points than the kernel can '
+                           'hold (the affected circumferences are NaN)')
     if return_points:
         return out, pts, cnt, status
     return out

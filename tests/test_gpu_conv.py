@@ -94,3 +94,45 @@ def test_unsupported_shape_is_reported():
         ops.conv_test(x, w, bn=bn, stride=1, relu=True, mode=1, engine=0)
     y = ops.conv_test(x, w, bn=bn, stride=1, relu=True, mode=1, engine=1)   # the SIMT engine handles it
     assert rel(y, _ref(x, w, None, bn, 1, None, True)) < 2e-5
+
+
+# the convolution families of the network at the batch sizes BASELINE's configurations run (halo_configure and the
+# per-tap tile chooser pick their tiles from the batch): (cin, cout, k, stride, H)
+BENCH_SHAPES = [(48, 48, 3, 1, 56), (96, 96, 3, 1, 28), (192, 192, 3, 1, 14), (384, 384, 3, 1, 7), (64, 64, 3, 1, 56),
+                (64, 256, 1, 1, 56), (256, 64, 1, 1, 56), (48, 96, 3, 2, 56), (96, 192, 3, 2, 28), (192, 384, 3, 2, 14),
+                (192, 48, 1, 1, 14), (2048, 512, 1, 1, 7)]
+
+
+@pytest.mark.parametrize('shape', BENCH_SHAPES)
+def test_conv_split_benchmark_batch(shape):
+    """configs[2] launch configurations: B = 64, split-fp16 mode, tcgen05 engine, with residual."""
+    from shapy_b200 import ops
+    cin, cout, k, stride, H = shape
+    x, w, bn, res = _case(cin, cout, k, stride, H, H, 64, seed=2)
+    ref = _ref(x, w, None, bn, stride, res, True)
+    y = ops.conv_test(x, w, bn=bn, stride=stride, res_nhwc=res, relu=True, mode=1, engine=0)
+    assert rel(y, ref) < 2e-5, rel(y, ref)
+
+
+@pytest.mark.parametrize('shape', BENCH_SHAPES)
+def test_conv_fp16_benchmark_batch(shape):
+    """configs[1] launch configurations: B = 32, plain fp16 operands.  Reference: the same operands rounded to fp16
+    (BN scale folded into the weights first, as the library does), fp32 accumulation; the library's output is itself
+    rounded to fp16, so every element must be within 1 fp16 ulp of the reference."""
+    from shapy_b200 import ops
+    cin, cout, k, stride, H = shape
+    x, w, bn, _ = _case(cin, cout, k, stride, H, H, 32, seed=3)
+    s = bn['weight'] / torch.sqrt(bn['var'] + bn['eps'])
+    wf = (w * s[:, None, None, None]).half().float()
+    shift = bn['bias'] - bn['mean'] * s
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(x.half().float().permute(0, 3, 1, 2), wf, None, stride=stride, padding=k // 2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    ref = F.relu(ref + shift[None, :, None, None]).permute(0, 2, 3, 1)
+    y = ops.conv_test(x, w, bn=bn, stride=stride, relu=True, mode=0, engine=0)
+    err = (y - ref).abs() / (ref.abs() + 1e-2)
+    assert float(err.max()) < 1.2e-3, float(err.max())          # 1 ulp of fp16 = 9.8e-4 relative
+    assert float(((y - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt()) < 4e-4

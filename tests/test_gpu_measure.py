@@ -64,7 +64,9 @@ def test_triangles_entry_matches_vertices_entry(data):
     a = ops.measure(ops.make_landmarks(lm), v_shaped=v, faces_i32=f)
     tris = v[:, f.long()]
     b = ops.measure(ops.make_landmarks(lm), triangles=tris.contiguous())
-    assert torch.equal(a, b)
+    # the two entries run different kernels (vertices staged in shared memory + 24-warp hull vs. the streaming v1
+    # kernel): same predicates and point sets, different fp32 summation orders
+    assert float(((a - b).abs() / b.abs()).max()) < 2e-6
 
 
 def test_module_api_and_batch_independence(data):
@@ -89,8 +91,9 @@ def test_module_api_and_batch_independence(data):
     b = ops.measure(ops.make_landmarks(lm), v_shaped=(one * s).contiguous(), faces_i32=f)[0]
     assert abs(b[0] / a[0] - s ** 3) < 1e-5 and abs(b[1] / a[1] - s) < 1e-6
     assert all(abs(b[i] / a[i] - s) < 2e-3 for i in (2, 3, 4))
-    out = bm(big[:2][:, f.long()].contiguous(), compute_mass=False)['measurements']
-    assert 'mass' not in out and torch.equal(out['hips']['tensor'], m['hips']['tensor'][:2])
+    out = bm(big[:2][:, f.long()].contiguous(), compute_mass=False)['measurements']    # triangles entry: v1 kernel
+    assert 'mass' not in out
+    assert float(((out['hips']['tensor'] - m['hips']['tensor'][:2]).abs() / m['hips']['tensor'][:2]).max()) < 2e-6
 
 
 def _sets(faces, bcs, Q, M):
