@@ -17,7 +17,13 @@ roofline: the dominant kernel is the tcgen05 implicit-GEMM convolution (HRNet = 
          achieved = algorithmic conv FLOPs (36.93 GFLOP / image @224^2) / HRNet device time.
          `roofline_lbs` / `roofline_shape` report the HBM rooflines of the fused SMPL-X kernels.
 cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, "port") timed on the
-         box's host cores on a bounded sample of the same workload.
+         box's host cores on a bounded sample of the same workload: one warm-up pass, then timed passes over the same
+         sample (the in-line cpu_baseline and the --impl reference arm use the same procedure).  The in-line leg
+         is also the bench's SELF-CHECK: the oracle's vertices / betas / measurements of the sampled images are
+         compared with the GPU outputs of the same images before anything is timed ("selfcheck" in the line).
+config2 : BASELINE configs[1] (HRNet-W48 only, plain fp16 operands, B = 32) timed in the same run.
+config5 : (N > 1) BASELINE configs[4]: rank 0 holds the whole batch (N x 64 uint8 images) in HBM, NCCL scatter ->
+         on-device crop / normalise -> forward -> NCCL gather of vertices / betas / measurements to rank 0.
 """
 import argparse
 import json
@@ -116,7 +122,8 @@ def cpu_reference_step(sd, smplx, lm, x):
         body = smplx_oracle.smplx_forward(smplx, p[:, 132:142], smplx_oracle.decode_6d(p[:, :6]),
                                           smplx_oracle.decode_6d(p[:, 6:132]))
     faces = smplx['faces_tensor'].numpy()
-    return [measure_oracle.measure(body['v_shaped'][b].numpy(), faces, lm) for b in range(x.shape[0])]
+    meas = [measure_oracle.measure(body['v_shaped'][b].numpy(), faces, lm) for b in range(x.shape[0])]
+    return dict(measurements=meas, vertices=body['vertices'], betas=p[:, 132:142])
 
 
 def run_reference(args):
@@ -144,10 +151,12 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = sample / dt
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'bodies/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'steps': args.steps, 'warmup': 1, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'configs[2]: full SHAPY_A regressor, 224x224, CPU port of the reference path',
-                       'sample': f'{sample} bodies per step'},
+            'config': {'workload': 'configs[2]: full SHAPY_A regressor, 224x224, CPU port of the reference path '
+                                   '(oracle/: the same ATen / oneDNN kernels the reference modules call)',
+                       'sample': f'{sample} bodies per step (per-body rate of the same workload; the GPU arm runs 64 per '
+                                 f'step), 1 warm-up pass of 1 body'},
             'cpu_baseline': {'value': v, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
                              'sample': f'{sample} images per step x {args.steps} steps (HRNet+head+SMPL-X+measurements)'},
             'e2e': {'value': v, 'unit': 'bodies/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -163,7 +172,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--batch', type=int, default=64, help='bodies per GPU')
     ap.add_argument('--mode', type=int, default=1, help='1 = split-fp16 parity mode (1e-4), 0 = plain fp16 (config 2)')
-    ap.add_argument('--ref-sample', type=int, default=4)
+    ap.add_argument('--ref-sample', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -244,18 +253,23 @@ def main():
     # separate streams; the bodies are independent, so there is no data-path collective.  All K batches (copies,
     # forwards, the L2 flush before each forward) sit inside ONE timed interval per rank; max over ranks.
     from shapy_b200.pipeline import HostPipeline
+    from shapy_b200.preprocess import InputStage
     per = B
-    full_host = torch.randn(per, 3, 224, 224, generator=g).pin_memory()
+    # the serving input: uint8 images in pinned host memory (what a decoder hands over) + the crop-descriptor table;
+    # crop / resize / normalisation run on the GPU inside the timed region (shapy_preprocess_forward)
+    stage = InputStage(dev, size=224)
+    u8_host = torch.randint(0, 256, (per, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    desc_host = stage.uniform_table(per, 224, 224)
     outs2 = [{'vertices': torch.empty(per, 10475, 3).pin_memory(), 'betas': torch.empty(per, 10).pin_memory(),
               'measurements': torch.empty(per, 5).pin_memory()} for _ in range(2)]
 
     def run_e2e(k):
-        pipe = HostPipeline(model, dev)
+        pipe = HostPipeline(model, dev, input_stage=stage)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(k):
-            pipe.submit(full_host, outs2[i % 2], between=flush.zero_)
+            pipe.submit_u8(u8_host, desc_host, outs2[i % 2], between=flush.zero_)
         pipe.drain()
         b.record()
         barrier()
@@ -265,11 +279,29 @@ def main():
         return float(t.item())
     run_e2e(W)
     e2e_ms = run_e2e(K) / K
-    e2e_mode = ('pipelined per rank: H2D / forward / D2H on three streams, K batches in one timed interval (L2 flush '
-                'included), max over ranks')
+    e2e_mode = ('pipelined per rank: H2D of uint8 images + crop descriptors / on-GPU crop+normalise + forward / D2H on three '
+                'streams, K batches in one timed interval (L2 flush included), max over ranks')
     e2e_value = world * B / (e2e_ms * 1e-3)
-    h2d = world * per * 3 * 224 * 224 * 4
+    h2d = world * (per * 224 * 224 * 3 + desc_host.numel())
     d2h = world * per * (10475 * 3 + 10 + 5) * 4
+
+    # ---------------------------------------------------------------- configs[4]: rank-0 batch, NCCL scatter / gather
+    cfg5 = None
+    if world > 1:
+        from shapy_b200 import dist as sdist
+        full_u8 = torch.randint(0, 256, (world * per, 224, 224, 3), dtype=torch.uint8, generator=g).to(dev) if rank == 0 else None
+
+        def step_cfg5():
+            return sdist.sharded_forward_u8(model, stage, full_u8, per, 224, 224, device=dev)
+        for _ in range(W):
+            step_cfg5()
+        c5_ms = timed(step_cfg5, K) / K
+        cfg5 = {'value': world * per / (c5_ms * 1e-3), 'unit': 'bodies/s', 'ms_per_batch': c5_ms, 'batch': world * per,
+                'scatter_bytes': (world - 1) * per * 224 * 224 * 3, 'gather_bytes': (world - 1) * per * (10475 * 3 + 10 + 5) * 4,
+                'path': 'rank 0 holds the uint8 batch in HBM -> dist.scatter (NCCL) -> shapy_preprocess_forward -> forward -> '
+                        'dist.gather of vertices / betas / measurements to rank 0; scatter, compute and gather run back to '
+                        'back on one stream (no overlap), device-timed per batch, max over ranks',
+                'limiter': 'the forward itself: rank-0 egress + ingress are < 3 % of the batch time at these sizes'}
 
     # ---------------------------------------------------------------- per-stage device times (rank 0, N = 1 view)
     line = None
@@ -310,20 +342,56 @@ def main():
         for _ in range(2):
             meas()
         meas_ms = timed(meas, 5) / 5
+        meas_gbs = (4096 * 125700 + faces.numel() * 4) / (meas_ms * 1e-3) / 1e9      # vertices once + the face table
+        # BASELINE configs[1]: HRNet-W48 only, plain fp16 operands, B = 32 (a second plan of the same weights)
+        import copy
+        bb16 = copy.deepcopy(bb)
+        bb16.precision_mode = 0
+        bb16.invalidate()
+        x32 = x_dev[:32].contiguous() if B >= 32 else torch.randn(32, 3, 224, 224, device=dev)
+
+        def hr16():
+            with torch.no_grad():
+                return bb16(x32)['concat']
+        for _ in range(3):
+            hr16()
+        hr16_ms = timed(hr16, 10) / 10
+        c2_tf = 32 * CONV_GFLOP_PER_IMAGE_224 * 1e9 / (hr16_ms * 1e-3) / 1e12
+        del bb16
 
     if rank == 0:
-        cpu = None
+        cpu, selfcheck = None, None
         if world == 1 and not args.no_cpu_baseline:
+            # One leg, two uses: (1) self-check -- the oracle's outputs for `n` of the step's images against the GPU outputs
+            # of the same images (taken from the full B = 64 forward), (2) cpu_baseline -- the same oracle passes timed
+            # with the procedure of the --impl reference arm: one warm-up pass, then `reps` timed passes.
             cores = usable_cores()
             torch.set_num_threads(cores)
             smplx, lm = synth.make_smplx(), synth.load_landmarks()
-            n = args.ref_sample
-            xs = x_host[:n].clone()
+            n = min(args.ref_sample, B)
+            rows = [int(round(i * (B - 1) / max(n - 1, 1))) for i in range(n)]
+            xs = x_host[rows].clone()
+            ref = cpu_reference_step(sd_cpu, smplx, lm, xs)                      # warm-up pass + self-check data
+            with torch.no_grad():
+                o = model(x_dev)
+            st = o[o['stage_keys'][-1]]
+
+            def rel(a, b):
+                return float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
+            errs = {'vertices': rel(st['vertices'][rows], ref['vertices']), 'betas': rel(st['betas'][rows], ref['betas'])}
+            for name in ('mass', 'height', 'chest', 'waist', 'hips'):
+                r = torch.tensor([m[name] for m in ref['measurements']], dtype=torch.float64)
+                errs[name] = float(((o['measurements'][name][rows].double().cpu() - r).abs() / r.abs()).max())
+            selfcheck = {'bodies': n, 'rows': rows, 'max_rel_err': max(errs.values()), 'errors': errs, 'tolerance': 1e-4}
+            assert selfcheck['max_rel_err'] < 1e-4, f'bench self-check failed: {errs}'
+            reps = 3
             t0 = time.perf_counter()
-            cpu_reference_step(sd_cpu, smplx, lm, xs)
-            dt = time.perf_counter() - t0
+            for _ in range(reps):
+                cpu_reference_step(sd_cpu, smplx, lm, xs)
+            dt = (time.perf_counter() - t0) / reps
             cpu = {'value': n / dt, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
-                   'sample': f'{n} of the {B} images of one step, one pass (HRNet+head+SMPL-X+measurements), {dt:.1f} s'}
+                   'sample': f'{n} of the {B} images of one step (HRNet+head+SMPL-X+measurements), 1 warm-up pass + {reps} timed '
+                             f'passes, {dt:.2f} s per pass'}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'bodies/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -339,16 +407,26 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': conv_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                          'frac': conv_tf / pk['tf_sustained'], 'traffic': conv_traffic(B, args.mode),
-                         'kernel': 'conv_umma_kernel (HRNet forward: all 331 convs + fuse + pool)',
+                         'kernel': 'conv_halo_kernel / conv_umma_kernel (HRNet forward: all 331 convs + fuse + pool, 4 lanes)',
                          'ms': hr_ms, 'mma_flops_factor': 3 if args.mode else 1, 'peak_source': pk['source']},
             'roofline_lbs': {'bound': 'hbm', 'achieved': lbs_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
-                             'frac': lbs_gbs / pk['hbm'], 'ms': lbs_ms, 'kernel': 'smplx_pose+vertex+joints, B=%d posed' % B},
+                             'frac': lbs_gbs / pk['hbm'], 'ms': lbs_ms, 'kernel': 'smplx_lbs_kernel (fused tcgen05) + smplx_joints_kernel, B=%d posed' % B},
             'roofline_shape': {'bound': 'hbm', 'achieved': shp_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
                                'frac': shp_gbs / pk['hbm'], 'ms': shp_ms, 'kernel': 'smplx_shape_kernel, 4096 bodies (config 4)'},
-            'measure_4096': {'ms': meas_ms, 'bodies_per_s': 4096 / (meas_ms * 1e-3)},
+            'roofline_measure': {'bound': 'hbm', 'achieved': meas_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
+                                 'frac': meas_gbs / pk['hbm'], 'ms': meas_ms, 'bodies_per_s': 4096 / (meas_ms * 1e-3),
+                                 'kernel': 'measure_smem_kernel, 4096 bodies (config 4): 125 700 B of vertices per body read once'},
+            'config2': {'workload': 'configs[1]: HRNet-W48 backbone only, 224x224, plain fp16 operands, batch 32',
+                        'ms': hr16_ms, 'images_per_s': 32 / (hr16_ms * 1e-3),
+                        'roofline': {'bound': 'tensor', 'achieved': c2_tf, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
+                                     'frac': c2_tf / pk['tf_sustained'], 'mma_flops_factor': 1}},
         }
+        if cfg5:
+            line['config5'] = cfg5
         if cpu:
             line['cpu_baseline'] = cpu
+        if selfcheck:
+            line['selfcheck'] = selfcheck
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

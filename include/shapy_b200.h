@@ -239,6 +239,18 @@ int shapy_b2a_forward(const float *betas, const int *gender, const float *w_male
                       const float *w_female, const float *b_female, int batch, int num_betas, int num_outputs, float *out,
                       void *stream);
 
+/* A2B head: attribute ratings (+ height / weight) -> betas, per gender.  Replaces
+ * regressor/human_shape/models/common/iterative_regressor.py:837-850 around A2B.forward
+ * (attributes/attributes/attributes_betas/a2b.py:278-279) for the `polynomial` (degree 2) and `linear` networks.
+ *   feat_male / feat_female : device (B, num_features) fp32 -- the reference builds one feature vector per gender
+ *                             (its default height / weight differ, iterative_regressor.py:793-836)
+ *   gender : device (B) int32, 0 = male, 1 = female, other = row of zeros
+ *   w_*    : device (num_betas, F) fp32 row-major, F = num_features (linear != 0) or num_features + num_features
+ *            (num_features + 1) / 2 (degree-2 polynomial);  b_* : device (num_betas);  out : device (B, num_betas) */
+int shapy_a2b_forward(const float *feat_male, const float *feat_female, const int *gender, const float *w_male,
+                      const float *b_male, const float *w_female, const float *b_female, int batch, int num_features,
+                      int num_betas, int linear, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Evaluation metric: translation-aligned point-to-point error through sparse point regressors
  * ("P2P-20k", also plain v2v with identity regressors).  Replaces regressor/human_shape/utils/metrics.py:368-456
@@ -252,6 +264,13 @@ int shapy_p2p_error(const int *in_row_ptr, const int *in_col, const float *in_va
                     const float *tg_val, const float *input_vertices, const float *target_vertices, int batch, int num_points,
                     int num_input_vertices, int num_target_vertices, int align, float *error, float *mean_error, void *workspace,
                     size_t workspace_bytes, void *stream);
+
+/* Vertex-to-vertex error between meshes of the SAME topology, translation aligned or not: PointError with
+ * TranslationAlignment / NoAlignment, regressor/human_shape/utils/metrics.py:232-277, 335-366 (evaluation.py:192-224
+ * `v2v_t` / `v2v`): est' = est + (mean(gt) - mean(est)); error[b][v] = |est'[b][v] - gt[b][v]|.
+ * input / target: device (B, V, 3) fp32; error (B, V), mean_error (B); workspace >= shapy_p2p_workspace_bytes(B, V). */
+int shapy_v2v_error(const float *input_vertices, const float *target_vertices, int batch, int num_verts, int align,
+                    float *error, float *mean_error, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

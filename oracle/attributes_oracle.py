@@ -51,3 +51,36 @@ def b2a_by_gender(betas, genders, male, female) -> np.ndarray:
     if len(f):
         out[f] = polynomial_forward(betas[f], *female)
     return out
+
+
+def a2b_features(rating, selected_idx, mmts: dict, selected_mmts, bodytalk_meas_preprocess: bool = False) -> np.ndarray:
+    """attributes/attributes/attributes_betas/a2b.py:569-592 (no noise): rating[:, selected] followed by one column per
+    selected measurement name (height * 100 and cube root of mass / weight under bodytalk_meas_preprocess)."""
+    fv = np.asarray(rating, np.float32)[:, list(selected_idx)]
+    for name in selected_mmts:
+        m = np.asarray(mmts[name], np.float32).reshape(-1, 1)
+        if bodytalk_meas_preprocess:
+            if 'height' in name:
+                m = m * 100
+            if 'mass' in name or 'weight' in name:
+                m = np.power(m, np.float32(1.0 / 3.0))
+        fv = np.hstack((fv, m))
+    return fv.astype(np.float32)
+
+
+def a2b_by_gender(feat_m, feat_f, genders, male, female, linear: bool = False) -> np.ndarray:
+    """regressor/human_shape/models/common/iterative_regressor.py:837-850: betas_ref rows of the males from
+    a2b_males(male features), of the females from a2b_females(female features), zeros elsewhere."""
+    g = np.array([x.lower()[0] if (x is not None and x != '') else 'n' for x in genders])
+    out = np.zeros((len(g), np.asarray(male[0]).shape[0]), np.float32)
+
+    def net(x, w, b):
+        if linear:
+            return (np.asarray(x, np.float64) @ np.asarray(w, np.float64).T + np.asarray(b, np.float64)).astype(np.float32)
+        return polynomial_forward(x, w, b)
+    m, f = np.where(g == 'm')[0], np.where(g == 'f')[0]
+    if len(m):
+        out[m] = net(np.asarray(feat_m)[m], *male)
+    if len(f):
+        out[f] = net(np.asarray(feat_f)[f], *female)
+    return out

@@ -33,3 +33,11 @@ def p2p_error(in_csr, tg_csr, input_vertices, target_vertices, align=True):
     diff = a + t[:, None, :] - c
     err = np.sqrt((diff ** 2).sum(-1))
     return err.mean(1), err
+
+
+def v2v_error(est, gt, align=True):
+    """PointError(TranslationAlignment() | NoAlignment()), regressor/human_shape/utils/metrics.py:232-277 + 31-52:
+    est' = est + (gt.mean(1) - est.mean(1)); error = sqrt(((est' - gt) ** 2).sum(-1)) -> (B, V), float64."""
+    est, gt = np.asarray(est, np.float64), np.asarray(gt, np.float64)
+    t = gt.mean(1, keepdims=True) - est.mean(1, keepdims=True) if align else 0.0
+    return np.sqrt(((est + t - gt) ** 2).sum(-1))

@@ -88,8 +88,10 @@ _SIGS = {
                                          c_void_p]),
     'shapy_b2a_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),
+    'shapy_a2b_forward': (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p, c_void_p]),
     'shapy_p2p_workspace_bytes': (c_size_t, [c_int, c_int]),
     'shapy_p2p_error': (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'shapy_v2v_error': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'shapy_conv_test': (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p]),
 }

@@ -63,6 +63,133 @@ class B2A(nn.Module):
         return self.b2a(x)
 
 
+# attribute vocabulary of the rating vectors (attributes/attributes/utils/constants.py:38-73): pure data, needed to turn
+# the `{gender}_attributes: {name: bool}` switches of an A2B checkpoint's config into indices of the rating vector
+ATTRIBUTE_NAMES = {
+    'female': ['Big', 'Broad Shoulders', 'Feminine', 'Large Breasts', 'Long Legs', 'Long Neck', 'Long Torso', 'Muscular',
+               'Pear Shaped', 'Petite', 'Short', 'Short Arms', 'Skinny Legs', 'Slim Waist', 'Tall'],
+    'male': ['Average', 'Big', 'Broad Shoulders', 'Delicate Build', 'Long Legs', 'Long Neck', 'Long Torso', 'Masculine',
+             'Muscular', 'Rectangular', 'Short', 'Short Arms', 'Skinny Arms', 'Soft Body', 'Tall'],
+}
+
+
+def features_from_config(cfg):
+    """attributes/attributes/utils/config.py:373-413 (non-synthetic datasets): (attribute names, their indices in the
+    rating vector, measurement feature names) switched on in an A2B config."""
+    ds_gender = cfg.get('ds_gender', 'female')
+    names = ATTRIBUTE_NAMES[ds_gender]
+    attributes = []
+    if cfg.get('use_attributes', True):
+        attributes = [k for k, v in (cfg.get(f'{ds_gender}_attributes') or {}).items() if v]
+    idx = [i for i, v in enumerate(names) if v.lower().replace(' ', '_') in attributes]
+    if len(idx) != len(attributes):
+        raise ValueError('Some selected attributes are not annotated.')
+    mmts = []
+    if cfg.get('use_measurements', True):
+        mmts = [k for k, v in (cfg.get('measurements') or {}).items() if v]
+    return attributes, idx, mmts
+
+
+class A2B(nn.Module):
+    """Attributes (+ height / weight) -> betas: host mirror of attributes/attributes/attributes_betas/a2b.py:91-279
+    (module), 569-602 (create_input_feature_vec) for the network types the released regressors use -- `polynomial`
+    (degree 2, polynomial.py) and `linear`.  The network is held as `.a2b` with the reference's parameter names, so a
+    Lightning checkpoint's `state_dict` loads unchanged; forward(x) = self.a2b(x) (a2b.py:278-279) runs on the device
+    through `shapy_b2a_forward` (the same degree-2 kernel as B2A, csrc/attributes.cu)."""
+
+    def __init__(self, cfg=None, input_dim=None, output_dim=None, network_type=None):
+        super().__init__()
+        cfg = cfg or {}
+        self.cfg = cfg
+        self.betas_size = int(output_dim or cfg.get('num_shape_comps', 10))
+        self.ds_gender = cfg.get('ds_gender', 'female')
+        self.bodytalk_meas_preprocess = bool(cfg.get('bodytalk_meas_preprocess', False))
+        if cfg.get('use_attr_noise', False) or cfg.get('use_srb_noise', False):
+            raise ValueError('shapy_b200 A2B: input-noise options are training-time features and are not supported')
+        if input_dim is None:
+            self.selected_attr, self.selected_attr_idx, self.selected_mmts = features_from_config(cfg)
+            input_dim = len(self.selected_attr) + len(self.selected_mmts)
+        else:
+            self.selected_attr, self.selected_attr_idx, self.selected_mmts = [], list(range(input_dim)), []
+        self.input_feature_size = int(input_dim)
+        ntype = network_type or (cfg.get('network') or {}).get('type', 'polynomial')
+        if ntype == 'polynomial':
+            degree = ((cfg.get('network') or {}).get('polynomial') or {}).get('degree', 2)
+            self.a2b = Polynomial(self.input_feature_size, self.betas_size, degree)
+        elif ntype == 'linear':
+            self.a2b = nn.Linear(self.input_feature_size, self.betas_size)
+        else:
+            raise NotImplementedError(f'shapy_b200 A2B: network type `{ntype}` is not on the released-model path '
+                                      '(polynomial / linear are)')
+        self.network_type = ntype
+
+    @staticmethod
+    def load_from_checkpoint(checkpoint_path, cfg=None, map_location='cpu'):
+        """Reads a Lightning checkpoint of the reference's A2B: `hyper_parameters['cfg']` + `state_dict` (`a2b.*`)."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        if cfg is None:
+            cfg = (ckpt.get('hyper_parameters') or {}).get('cfg', {})
+        obj = A2B(cfg)
+        sd = ckpt['state_dict'] if 'state_dict' in ckpt else ckpt
+        obj.load_state_dict({k: v for k, v in sd.items() if k.startswith('a2b.')}, strict=True)
+        return obj.eval()
+
+    def create_input_feature_vec(self, batch):
+        """a2b.py:569-602 without the training-time noise: [rating[:, selected] | one column per selected measurement]."""
+        fv = batch['rating'][:, self.selected_attr_idx]
+        if not torch.is_tensor(fv):
+            fv = torch.from_numpy(np.asarray(fv)).to(dtype=torch.float32)
+        noise = torch.zeros_like(fv)
+        for name in self.selected_mmts:
+            meas = batch[name].reshape(-1, 1)
+            if not torch.is_tensor(meas):
+                meas = torch.from_numpy(np.asarray(meas)).to(dtype=torch.float32)
+            meas = meas.to(device=fv.device, dtype=fv.dtype)
+            if self.bodytalk_meas_preprocess:
+                if 'height' in name:
+                    meas = meas * 100
+                if 'mass' in name or 'weight' in name:
+                    meas = meas.pow(1.0 / 3.0)
+            fv = torch.hstack((fv, meas))
+        return fv, noise
+
+    def forward(self, x):
+        g = torch.zeros(x.shape[0], dtype=torch.int32, device=x.device)
+        return a2b_forward(x, g, self, self)
+
+
+def _a2b_wb(module):
+    net = module.a2b if isinstance(module, A2B) else module
+    if isinstance(net, Polynomial):
+        return net.linear.weight, net.linear.bias, net.input_dim, True
+    return net.weight, net.bias, net.in_features, False
+
+
+def a2b_forward(features_m: torch.Tensor, gender, males, females, features_f: torch.Tensor = None):
+    """(B, num_betas): rows of gender 0 go through `males` with `features_m`, rows of gender 1 through `females` with
+    `features_f` (the reference builds one feature vector per gender, iterative_regressor.py:808-836); other rows are
+    zero (843-850).  One launch of `shapy_a2b_forward`."""
+    features_f = features_m if features_f is None else features_f
+    if not (torch.is_tensor(features_m) and features_m.is_cuda and features_f.is_cuda):
+        raise RuntimeError('shapy_b200.attributes: features must be CUDA tensors (there is no CPU fallback)')
+    dev = features_m.device
+    wm, bm, n, poly = _a2b_wb(males)
+    wf, bf, nf, polyf = _a2b_wb(females)
+    if n != nf or wm.shape != wf.shape or poly != polyf:
+        raise ValueError('male and female A2B regressors must have the same architecture')
+    if features_m.shape[1] != n or features_f.shape != features_m.shape:
+        raise ValueError(f'A2B expects {n} input features per gender, got {tuple(features_m.shape)} / {tuple(features_f.shape)}')
+    gender = torch.as_tensor(gender).to(device=dev, dtype=torch.int32).contiguous()
+    ws = [t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in (wm, bm, wf, bf)]
+    fm, ff = features_m.contiguous().float(), features_f.contiguous().float()
+    out = torch.empty(fm.shape[0], wm.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().shapy_a2b_forward(_lib.ptr(fm), _lib.ptr(ff), _lib.ptr(gender), _lib.ptr(ws[0]), _lib.ptr(ws[1]),
+                                                _lib.ptr(ws[2]), _lib.ptr(ws[3]), fm.shape[0], n, wm.shape[0], 0 if poly else 1,
+                                                _lib.ptr(out), _lib.stream_ptr()), 'a2b_forward')
+    return out
+
+
 def gender_codes(targets, batch_size: int) -> np.ndarray:
     """iterative_regressor.py:762-767: first letter of the target's `gender` field -> 0 male, 1 female, 2 none."""
     genders = []

@@ -451,7 +451,7 @@ static int launch_measure(MeasureArgs a, void *stream) {
   static const bool v1_only = []() { const char *e = getenv("SHAPY_MEASURE_V1"); return e && e[0] == '1'; }();
   if (a.verts && !v1_only && a.V < 65536 && measure_smem_bytes(a.V) <= 220 * 1024) {
     static std::atomic<unsigned long long> attr_done{0};
-    SHAPY_CUDA_TRY(set_max_dynamic_smem(measure_smem_kernel, 227 * 1024, attr_done));
+    SHAPY_CUDA_TRY(set_max_dynamic_smem(measure_smem_kernel, 226 * 1024, attr_done));   // + 560 B static <= 227 KB
     measure_smem_kernel<<<a.B, kM2Threads, measure_smem_bytes(a.V), (cudaStream_t)stream>>>(a);
     SHAPY_LAUNCH_CHECK();
     return SHAPY_OK;

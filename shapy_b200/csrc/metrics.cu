@@ -22,6 +22,13 @@ __global__ void __launch_bounds__(256) p2p_diff_kernel(const int *__restrict__ r
   o[0] = a[0] - c[0]; o[1] = a[1] - c[1]; o[2] = a[2] - c[2];
 }
 
+// same-topology variant (PointError with TranslationAlignment / NoAlignment, metrics.py:232-277, 335-366): d = est - gt
+__global__ void __launch_bounds__(256) v2v_diff_kernel(const float *__restrict__ v_in, const float *__restrict__ v_tg, size_t n,
+                                                       float *__restrict__ d) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = v_in[i] - v_tg[i];
+}
+
 // one block per body: t = -mean_p d  (= mean target - mean input), or 0 without alignment
 __global__ void __launch_bounds__(256) p2p_translation_kernel(const float *__restrict__ d, int P, int align, float *__restrict__ t) {
   __shared__ float s[3][256];
@@ -87,6 +94,24 @@ extern "C" int shapy_p2p_error(const int *in_row_ptr, const int *in_col, const f
   p2p_translation_kernel<<<B, 256, 0, st>>>(d, P, align, t);
   SHAPY_LAUNCH_CHECK();
   p2p_error_kernel<<<B, 256, 0, st>>>(d, t, P, error, mean_error);
+  SHAPY_LAUNCH_CHECK();
+  return SHAPY_OK;
+}
+
+extern "C" int shapy_v2v_error(const float *input_vertices, const float *target_vertices, int B, int V, int align, float *error,
+                               float *mean_error, void *workspace, size_t workspace_bytes, void *stream) {
+  SHAPY_REQUIRE(input_vertices && target_vertices && error && mean_error && workspace, "shapy_v2v_error: null argument");
+  SHAPY_REQUIRE(B > 0 && B <= 65535 && V > 0, "shapy_v2v_error: bad sizes");
+  SHAPY_REQUIRE(workspace_bytes >= shapy_p2p_workspace_bytes(B, V), "shapy_v2v_error: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *d = (float *)workspace;
+  float *t = d + (size_t)B * V * 3;
+  const size_t n = (size_t)B * V * 3;
+  v2v_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(input_vertices, target_vertices, n, d);
+  SHAPY_LAUNCH_CHECK();
+  p2p_translation_kernel<<<B, 256, 0, st>>>(d, V, align, t);
+  SHAPY_LAUNCH_CHECK();
+  p2p_error_kernel<<<B, 256, 0, st>>>(d, t, V, error, mean_error);
   SHAPY_LAUNCH_CHECK();
   return SHAPY_OK;
 }

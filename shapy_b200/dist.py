@@ -55,3 +55,40 @@ def sharded_forward(model, images, per_rank: int, shape=(3, 224, 224), device=No
     res = dict(vertices=st['vertices'], v_shaped=st['v_shaped'], betas=st['betas'], joints=st['joints']._t,
                measurements=meas)
     return gather_results(res, dst=src)
+
+
+def scatter_bytes(data_u8, nbytes_per_rank: int, device, src: int = 0):
+    """rank `src` passes a uint8 tensor of world * nbytes_per_rank bytes (rank r's shard at [r * n, (r + 1) * n)), the
+    others None; returns the local shard as a flat uint8 tensor on `device`."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    local = torch.empty(nbytes_per_rank, dtype=torch.uint8, device=device)
+    if world == 1:
+        local.copy_(data_u8.reshape(-1))
+        return local
+    chunks = list(data_u8.reshape(world, nbytes_per_rank).unbind(0)) if rank == src else None
+    dist.scatter(local, chunks, src=src)
+    return local
+
+
+def sharded_forward_u8(model, input_stage, images_u8, per_rank: int, height: int, width: int, device=None, src: int = 0,
+                       keys=('vertices', 'betas', 'measurements')):
+    """BASELINE configs[4] as a call: rank `src` holds the whole batch as uint8 images (world * per_rank, H, W, 3)
+    on its device (None elsewhere).  Scatter ships ONE byte per channel over NVLink (4x less rank-0 egress than fp32
+    crops: 512 images = 77 MB instead of 308 MB), every rank crops / resizes / normalises its shard on the device
+    (`shapy_preprocess_forward`), runs the regressor, and the per-body results named by `keys` are gathered back to
+    `src` in global batch order.  Returns the gathered dict on `src`, None elsewhere."""
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    local = scatter_bytes(images_u8, per_rank * height * width * 3, device, src)
+    key = (per_rank, height, width, str(device))
+    cache = getattr(input_stage, '_dist_tables', None)
+    if cache is None:
+        cache = input_stage._dist_tables = {}
+    if key not in cache:
+        cache[key] = input_stage.uniform_table(per_rank, height, width).to(device)
+    with torch.no_grad():
+        x = input_stage.run_device(local, cache[key], per_rank)
+        out = model(x)
+    st = out[out['stage_keys'][-1]]
+    res = dict(vertices=st['vertices'], v_shaped=st['v_shaped'], betas=st['betas'], joints=st['joints']._t,
+               measurements=torch.stack([out['measurements'][k] for k in ('mass', 'height', 'chest', 'waist', 'hips')], dim=1))
+    return gather_results({k: res[k] for k in keys}, dst=src)

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops as _ops
-from ....attributes import B2A, b2a_forward, gender_codes
+from ....attributes import A2B, B2A, a2b_forward, b2a_forward, gender_codes
 from ....body_measurements import BodyMeasurements
 from ..backbone.build import build_backbone
 from ..body_models.utils import KeypointTensor
@@ -79,9 +79,19 @@ class HMRLikeRegressor(nn.Module):
             for mod in (self.b2a_males, self.b2a_females):
                 for p in mod.parameters():
                     p.requires_grad = False
-        if network_cfg.get('use_a2b', False) and osp.exists(osp.expandvars(network_cfg.get('a2b_males_checkpoint', '') or '')):
-            raise NotImplementedError('shapy_b200: the A2B head (iterative_regressor.py:173-204, 778-852) is not built')
-        self.use_a2b = False
+        # attributes (+ height / weight) -> betas regressors, one per gender (iterative_regressor.py:173-204)
+        a2b_m = osp.expandvars(network_cfg.get('a2b_males_checkpoint', '') or '')
+        a2b_f = osp.expandvars(network_cfg.get('a2b_females_checkpoint', '') or '')
+        self.num_attributes = network_cfg.get('num_attributes', False)
+        self.use_a2b = bool(network_cfg.get('use_a2b', False)) and osp.exists(a2b_m) and osp.exists(a2b_f)
+        if self.use_a2b:
+            if not self.compute_measurements:
+                raise ValueError('shapy_b200: use_a2b needs compute_measurements (height_bg / weight_bg features)')
+            self.a2b_males = A2B.load_from_checkpoint(a2b_m)
+            self.a2b_females = A2B.load_from_checkpoint(a2b_f)
+            for mod in (self.a2b_males, self.a2b_females):
+                for p in mod.parameters():
+                    p.requires_grad = False
 
     # properties of the reference class
     param_dim = property(lambda self: self._param_dim)
@@ -151,5 +161,37 @@ class HMRLikeRegressor(nn.Module):
         if self.use_b2a:
             codes = torch.from_numpy(gender_codes(targets, batch_size))
             out_params['attributes'] = b2a_forward(merged['betas'], codes, self.b2a_males, self.b2a_females)
+        if self.use_a2b:
+            self._a2b(out_params, targets, batch_size, last, images.device)
         out_params['losses'] = {}
         return out_params
+
+    def _a2b(self, out_params, targets, batch_size, last, device):
+        """iterative_regressor.py:778-852: refined betas from the attribute ratings + height / weight of the targets
+        (missing values default to 1.71 m / 71 kg for the male and 1.59 m / 62 kg for the female regressor) and the
+        measured height / mass of the predicted body; then only the shape blend (`forward_shape`)."""
+        targets = list(targets) if targets is not None else []
+        targets = (targets + [None] * batch_size)[:batch_size]
+
+        def field(t, name, default):
+            if t is not None and hasattr(t, 'get_field'):
+                try:
+                    return t.get_field(name, default)
+                except TypeError:
+                    return t.get_field(name) if t.has_field(name) else default
+            return default
+        n_attr = int(self.num_attributes or len(self.a2b_males.selected_attr_idx) or 15)
+        attr = torch.stack([torch.as_tensor(t.get_field('attributes'), dtype=torch.float32)
+                            if (t is not None and t.has_field('attributes')) else torch.zeros(n_attr) for t in targets]).to(device)
+        meas = out_params['measurements']
+        vecs = {}
+        for g, mod, h0, w0 in (('m', self.a2b_males, 1.71, 71.0), ('f', self.a2b_females, 1.59, 62.0)):
+            batch = {'rating': attr,
+                     'height_gt': torch.tensor([field(t, 'height', h0) for t in targets], dtype=torch.float32, device=device),
+                     'weight_gt': torch.tensor([field(t, 'weight', w0) for t in targets], dtype=torch.float32, device=device),
+                     'height_bg': meas['height'], 'weight_bg': meas['mass']}
+            vecs[g], _ = mod.create_input_feature_vec(batch)
+        codes = torch.from_numpy(gender_codes(targets, batch_size))
+        betas_ref = a2b_forward(vecs['m'], codes, self.a2b_males, self.a2b_females, vecs['f'])
+        out_params[last]['betas_ref'] = betas_ref
+        out_params[last]['v_shaped_ref'] = self.model.forward_shape(betas_ref)['v_shaped']

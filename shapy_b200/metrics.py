@@ -67,3 +67,67 @@ class v2vhdError(nn.Module):
                                          _lib.ptr(vt), B, P, V1, V2, int(bool(self.align)), _lib.ptr(error), _lib.ptr(mean), _lib.ptr(ws),
                                          nbytes, _lib.stream_ptr()), 'p2p_error')
         return mean, error
+
+
+class NoAlignment:
+    """metrics.py:85-98."""
+    name = 'none'
+
+    def __repr__(self):
+        return 'NoAlignment'
+
+
+class TranslationAlignment:
+    """metrics.py:232-277: est + (mean(gt) - mean(est))."""
+    name = 'translation'
+
+    def __repr__(self):
+        return 'ScaleAlignment'       # sic: the reference's __repr__ (metrics.py:236-237)
+
+
+def build_alignment(name: str, **kwargs):
+    """metrics.py:14-29 for the alignments evaluated on the device; Procrustes / root / scale are not built."""
+    if name == 'translation':
+        return TranslationAlignment()
+    if name in ('no', 'none'):
+        return NoAlignment()
+    raise NotImplementedError(f'shapy_b200.metrics: alignment `{name}` is not built (translation / none are)')
+
+
+class PointError:
+    """metrics.py:335-366 for same-topology meshes on the device: `PointError(build_alignment('translation'))(est, gt)`
+    returns the (B, V) per-vertex error the reference's `_compute_v2v` stores (evaluation.py:192-224), as a CUDA fp32
+    tensor; `.last_mean` keeps the per-body mean of the same launch.  The reference copies both meshes to the host."""
+
+    def __init__(self, alignment_object, name: str = ''):
+        if not isinstance(alignment_object, (TranslationAlignment, NoAlignment)):
+            raise NotImplementedError('shapy_b200 PointError: only translation / no alignment run on the device')
+        self._alignment, self._name, self.last_mean = alignment_object, name, None
+
+    name = property(lambda self: self._name)
+
+    def __repr__(self):
+        return f'PointError: Alignment = {self._alignment}'
+
+    def set_alignment(self, alignment_object):
+        self.__init__(alignment_object, self._name)
+
+    def __call__(self, est_points, gt_points):
+        for nm, t in (('est_points', est_points), ('gt_points', gt_points)):
+            if not (torch.is_tensor(t) and t.is_cuda):
+                raise RuntimeError(f'shapy_b200 PointError: {nm} must be a CUDA tensor (there is no CPU fallback)')
+        if est_points.shape != gt_points.shape or est_points.dim() != 3 or est_points.shape[2] != 3:
+            raise ValueError('PointError: expected two (B, P, 3) tensors of the same shape')
+        dev = est_points.device
+        a, b = est_points.contiguous().float(), gt_points.to(dev).contiguous().float()
+        B, V = a.shape[:2]
+        error = torch.empty(B, V, dtype=torch.float32, device=dev)
+        mean = torch.empty(B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L = _lib.lib()
+            nbytes = L.shapy_p2p_workspace_bytes(B, V)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.shapy_v2v_error(_lib.ptr(a), _lib.ptr(b), B, V, int(isinstance(self._alignment, TranslationAlignment)),
+                                         _lib.ptr(error), _lib.ptr(mean), _lib.ptr(ws), nbytes, _lib.stream_ptr()), 'v2v_error')
+        self.last_mean = mean
+        return error

@@ -23,10 +23,13 @@ def pack_result(o) -> Dict[str, torch.Tensor]:
 class HostPipeline:
     """model: a shapy_b200 regressor on `device`; depth input slots (2 = double buffering)."""
 
-    def __init__(self, model, device, depth: int = 2):
+    def __init__(self, model, device, depth: int = 2, input_stage=None):
         if torch.device(device).type != 'cuda':
             raise RuntimeError('HostPipeline needs a CUDA device (there is no CPU path)')
         self.model, self.device, self.depth = model, torch.device(device), depth
+        self.input_stage = input_stage     # shapy_b200.preprocess.InputStage: enables submit_u8()
+        self.u8_slots = [None] * depth
+        self.desc_slots = [None] * depth
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self.slots: List[Optional[torch.Tensor]] = [None] * depth
@@ -55,6 +58,47 @@ class HostPipeline:
             between()
         with torch.no_grad():
             res = pack_result(self.model(self.slots[slot]))
+        self.slot_free[slot].record(cur)
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            for k, t in res.items():
+                t.record_stream(self.s_out)
+                out_host[k].copy_(t, non_blocking=True)
+            self.last_out.record(self.s_out)
+        self.n += 1
+
+    def submit_u8(self, images_u8_host: torch.Tensor, desc_host: torch.Tensor, out_host: Dict[str, torch.Tensor],
+                  between: Optional[Callable[[], None]] = None):
+        """uint8 entry: pinned host uint8 image bytes + the pinned crop-descriptor table of
+        `InputStage` (uniform_table / pack) cross PCIe (4x fewer bytes than fp32 crops); crop, resize and normalisation
+        run on the device (`shapy_preprocess_forward`) on the compute stream in front of the forward."""
+        if self.input_stage is None:
+            raise RuntimeError('HostPipeline.submit_u8 needs an InputStage (input_stage=...)')
+        if not (images_u8_host.is_pinned() and desc_host.is_pinned()):
+            raise ValueError('HostPipeline.submit_u8: images and descriptors must be in pinned host memory')
+        import ctypes as C
+        from . import _lib
+        n = desc_host.numel() // C.sizeof(_lib.ImageDesc)
+        cur = torch.cuda.current_stream(self.device)
+        slot = self.n % self.depth
+        if self.u8_slots[slot] is None or self.u8_slots[slot].numel() != images_u8_host.numel():
+            self.u8_slots[slot] = torch.empty(images_u8_host.numel(), dtype=torch.uint8, device=self.device)
+        if self.desc_slots[slot] is None or self.desc_slots[slot].numel() != desc_host.numel():
+            self.desc_slots[slot] = torch.empty(desc_host.numel(), dtype=torch.uint8, device=self.device)
+        with torch.cuda.stream(self.s_in):
+            if self.n >= self.depth:
+                self.s_in.wait_event(self.slot_free[slot])
+            self.u8_slots[slot].copy_(images_u8_host.reshape(-1), non_blocking=True)
+            self.desc_slots[slot].copy_(desc_host, non_blocking=True)
+            self.in_ready[slot].record(self.s_in)
+        cur.wait_event(self.in_ready[slot])
+        if between is not None:
+            between()
+        with torch.no_grad():
+            x = self.input_stage.run_device(self.u8_slots[slot], self.desc_slots[slot], n)
+            res = pack_result(self.model(x))
         self.slot_free[slot].record(cur)
         done = torch.cuda.Event()
         done.record(cur)

@@ -104,6 +104,33 @@ class InputStage:
             table[i].ul_x, table[i].ul_y, table[i].br_x, table[i].br_y = int(ul[0]), int(ul[1]), int(br[0]), int(br[1])
         return self._host[:total], self._hdesc[:nbytes]
 
+    def uniform_table(self, n: int, height: int, width: int, center=None, scale=None) -> torch.Tensor:
+        """Pinned descriptor table (as uint8) for `n` images of one size stored back to back, one person per image
+        (default: the window of a detection that covers the whole image) -- the layout a serving loop or the
+        rank-0 scatter of `shapy_b200.dist` ships."""
+        center = (width / 2.0, height / 2.0) if center is None else center
+        scale = max(height, width) / 200.0 if scale is None else scale
+        ul, br = crop_window(center, scale, self.size)
+        nbytes = n * C.sizeof(_lib.ImageDesc)
+        buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        table = (_lib.ImageDesc * n).from_buffer(buf.numpy())
+        for i in range(n):
+            table[i].offset, table[i].height, table[i].width = i * height * width * 3, height, width
+            table[i].ul_x, table[i].ul_y, table[i].br_x, table[i].br_y = int(ul[0]), int(ul[1]), int(br[0]), int(br[1])
+        return buf
+
+    def run_device(self, dimg: torch.Tensor, ddesc: torch.Tensor, n: int, out: torch.Tensor = None) -> torch.Tensor:
+        """Device-resident entry: `dimg` uint8 image bytes, `ddesc` the descriptor table (uint8 view), both already on
+        the device; launches the kernel on the current stream."""
+        if not (dimg.is_cuda and ddesc.is_cuda and dimg.dtype == torch.uint8):
+            raise RuntimeError('InputStage.run_device: device uint8 tensors expected (there is no CPU path)')
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(n, 3, self.size, self.size, dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib().shapy_preprocess_forward(_lib.ptr(dimg), _lib.ptr(ddesc), n, self.size, self.mean, self.std,
+                                                           _lib.ptr(out), _lib.stream_ptr()), 'preprocess_forward')
+        return out
+
     def __call__(self, images, persons) -> torch.Tensor:
         """(len(persons), 3, size, size) fp32 on the device, on the current stream."""
         if len(persons) == 0 or len(images) == 0:

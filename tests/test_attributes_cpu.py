@@ -67,3 +67,30 @@ def test_mirror_names_and_lightning_checkpoint_loading(tmp_path):
     with pytest.raises(RuntimeError):
         loaded(torch.zeros(2, 10))               # CPU tensors: no fallback
     assert attributes.gender_codes(None, 3).tolist() == [2, 2, 2]
+
+
+def test_a2b_host_logic(tmp_path):
+    """A2B mirror, host side: attribute selection from a checkpoint's config (config.py:373-413), feature vector
+    (a2b.py:569-592) against the oracle restatement, checkpoint round trip with the reference's `a2b.*` names."""
+    import torch
+    from oracle import attributes_oracle as ao2
+    from shapy_b200 import attributes
+    cfg = {'ds_gender': 'female', 'female_attributes': {'big': True, 'pear_shaped': True, 'tall': True, 'petite': False},
+           'measurements': {'height_gt': True, 'weight_gt': False, 'weight_bg': True}, 'bodytalk_meas_preprocess': True,
+           'network': {'type': 'polynomial'}}
+    m = attributes.A2B(cfg)
+    assert m.selected_attr_idx == [0, 8, 14] and m.selected_mmts == ['height_gt', 'weight_bg'] and m.input_feature_size == 5
+    assert m.a2b.linear.weight.shape == (10, 5 + 15)
+    rating = torch.rand(4, 15)
+    mm = {'height_gt': torch.tensor([1.6, 1.7, 1.8, 1.9]), 'weight_bg': torch.tensor([50., 60., 70., 80.])}
+    fv, noise = m.create_input_feature_vec({'rating': rating, **mm})
+    ref = ao2.a2b_features(rating.numpy(), [0, 8, 14], {k: v.numpy() for k, v in mm.items()}, ['height_gt', 'weight_bg'], True)
+    assert np.abs(fv.numpy() - ref).max() < 1e-5 and float(noise.abs().max()) == 0.0
+    path = str(tmp_path / 'a2b.ckpt')
+    torch.save({'state_dict': {f'a2b.{k}': v for k, v in m.a2b.state_dict().items()}, 'hyper_parameters': {'cfg': cfg}}, path)
+    m2 = attributes.A2B.load_from_checkpoint(path)
+    assert torch.equal(m2.a2b.linear.weight, m.a2b.linear.weight) and m2.selected_mmts == m.selected_mmts
+    with pytest.raises(ValueError):
+        attributes.A2B({**cfg, 'female_attributes': {'no_such_attribute': True}})
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 5))                 # CPU tensors: there is no CPU path for the regression itself

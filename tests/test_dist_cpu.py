@@ -32,6 +32,11 @@ def _worker(rank, world, port, ret):
             ok = ok and torch.equal(res['v'], ref.sum(dim=(1, 2, 3)).view(-1, 1)) and torch.equal(res['b'], ref[:, 0, 0])
         else:
             ok = ok and res['v'] is None
+        # uint8 scatter used by the configs[4] path (sharded_forward_u8): shards arrive in rank order, byte exact
+        nb = 5 * 4 * 4 * 3
+        allb = (torch.arange(world * nb) % 251).to(torch.uint8) if rank == 0 else None
+        mine = sdist.scatter_bytes(allb, nb, torch.device('cpu'))
+        ok = ok and torch.equal(mine, ((torch.arange(world * nb) % 251).to(torch.uint8))[rank * nb:(rank + 1) * nb])
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -30,6 +30,21 @@ def _worker(rank, world, port, ret):
                 ok = ok and torch.equal(res['betas'][r * per:(r + 1) * per], o['stage_02']['betas'])
                 ok = ok and torch.equal(res['measurements'][r * per:(r + 1) * per, 2], o['measurements']['chest'])
             ret[0] = bool(ok)
+        # configs[4] path: rank 0 holds uint8 images, scatter ships bytes, every rank preprocesses on the device
+        from shapy_b200.preprocess import InputStage
+        stage = InputStage(dev)
+        u8 = torch.randint(0, 256, (world * per, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(1))
+        res8 = sdist.sharded_forward_u8(model, stage, u8.to(dev) if rank == 0 else None, per, 224, 224, device=dev)
+        if rank == 0:
+            ok8 = True
+            for r in range(world):
+                shard = u8[r * per:(r + 1) * per].to(dev)
+                x = stage.run_device(shard.reshape(-1), stage.uniform_table(per, 224, 224).to(dev), per)
+                with torch.no_grad():
+                    o = model(x)
+                ok8 = ok8 and torch.equal(res8['vertices'][r * per:(r + 1) * per], o['stage_02']['vertices'])
+                ok8 = ok8 and torch.equal(res8['betas'][r * per:(r + 1) * per], o['stage_02']['betas'])
+            ret[1] = bool(ok8)
     finally:
         dist.destroy_process_group()
 
@@ -40,3 +55,4 @@ def test_sharded_forward_matches_single_gpu():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, 29500 + (os.getpid() % 2000), ret), nprocs=2, join=True)
     assert ret.get(0) is True
+    assert ret.get(1) is True

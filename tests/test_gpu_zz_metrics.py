@@ -32,3 +32,18 @@ def test_metric_matches_reference(tmp_path, align, tag):
     # the reference works in float64; fp32 points of magnitude ~1 give errors to ~1e-6 relative
     assert np.abs(mean - G[f'mean_{tag}']).max() / G[f'mean_{tag}'].max() < 1e-5
     assert np.abs(err - G[f'error_{tag}']).max() / G[f'error_{tag}'].max() < 1e-5
+
+
+@pytest.mark.parametrize('name,tag', [('translation', 'aligned'), ('none', 'raw')])
+def test_v2v_point_error_matches_reference(name, tag):
+    """shapy_v2v_error through the PointError mirror against the reference's PointError outputs (`v2v_t` / `v2v`)."""
+    from shapy_b200 import metrics
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'v2v.npz'))
+    pe = metrics.PointError(metrics.build_alignment(name))
+    err = pe(torch.from_numpy(g['est']).cuda(), torch.from_numpy(g['gt']).cuda())
+    ref = g[f'error_{tag}']
+    assert err.shape == ref.shape
+    assert np.abs(err.cpu().numpy() - ref).max() / ref.max() < 2e-5      # both sides fp32: eps * |coordinate| / error
+    assert np.abs(pe.last_mean.cpu().numpy() - ref.mean(1)).max() / ref.mean(1).max() < 2e-5
+    with pytest.raises(NotImplementedError):
+        metrics.build_alignment('procrustes')

@@ -54,3 +54,13 @@ def test_module_mirror_buffers_and_cpu_refusal(tmp_path):
     assert m.input_point_regressor.is_sparse and tuple(m.input_point_regressor.shape) == (len(IN[0]) - 1, G['v_in'].shape[1])
     with pytest.raises(RuntimeError):
         m(torch.from_numpy(G['v_in']), torch.from_numpy(G['v_tg']))
+
+
+@pytest.mark.parametrize('align,tag', [(True, 'aligned'), (False, 'raw')])
+def test_v2v_oracle_matches_reference_point_error(align, tag):
+    """metrics_oracle.v2v_error against the reference's own PointError(TranslationAlignment | NoAlignment) outputs
+    (tests/golden/v2v.npz, tools/make_golden.py v2v)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'v2v.npz'))
+    err = mo.v2v_error(g['est'], g['gt'], align)
+    assert err.shape == g[f'error_{tag}'].shape
+    assert np.abs(err - g[f'error_{tag}']).max() / g[f'error_{tag}'].max() < 5e-6     # the reference works in float32 here: eps * |coordinate| / error

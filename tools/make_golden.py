@@ -20,6 +20,7 @@ Everything written here is a small fixture that travels to the GPU box, where
   ref_measure.json      oracle/measure (quirk-faithful op.cu emulation) results on the 4 real bodies
   b2a.npz               reference Polynomial (B2A head) outputs with seeded male / female weights, routed by gender
   p2p.npz               reference v2vhdError (P2P metric) outputs on seeded sparse point regressors and meshes
+  v2v.npz               reference PointError(TranslationAlignment / NoAlignment) outputs (`v2v_t` / `v2v`) on two seeded meshes
   preprocess.npz        reference input stage (transf_utils.crop with cv2 + ToTensor + Normalize) on seeded uint8 images:
                         crop windows, crops with OpenCV's portable path (IPP off) and with this container's IPP build
 """
@@ -224,17 +225,14 @@ def b2a_fixture():
     print('b2a.npz', os.path.getsize(os.path.join(G, 'b2a.npz')), 'bytes')
 
 
-def p2p_fixture():
-    """Runs the reference's own v2vhdError (regressor/human_shape/utils/metrics.py:368-456, loaded by path behind stubs of
-    open3d / .np_utils / .typing) on seeded sparse point regressors (3 barycentric weights per point) and meshes, in
-    float64 on the CPU as the evaluator does (evaluation.py:258-260)."""
+def _load_ref_metrics():
+    """The reference's regressor/human_shape/utils/metrics.py loaded by path behind stubs of open3d / .np_utils / .typing."""
     import importlib.util
-    import pickle
-    import tempfile
     import types
-    import scipy.sparse as sp
     from loguru import logger
     logger.remove()
+    if 'ref_hs.utils.metrics' in sys.modules:
+        return sys.modules['ref_hs.utils.metrics']
     for name in ('open3d', 'ref_hs', 'ref_hs.utils', 'ref_hs.utils.np_utils', 'ref_hs.utils.typing'):
         m = types.ModuleType(name)
         m.__path__ = []
@@ -247,6 +245,33 @@ def p2p_fixture():
     mod.__package__ = 'ref_hs.utils'
     sys.modules['ref_hs.utils.metrics'] = mod
     spec.loader.exec_module(mod)
+    return mod
+
+
+def v2v_fixture():
+    """Runs the reference's own PointError with TranslationAlignment / NoAlignment (metrics.py:232-277, 335-366), i.e. the
+    `v2v_t` / `v2v` evaluation metrics (evaluation.py:192-224, 595-602), on two seeded meshes of the same topology."""
+    mod = _load_ref_metrics()
+    rng = np.random.default_rng(78)
+    B, V = 3, 1500
+    est = rng.normal(0, 0.4, (B, V, 3)).astype(np.float32)
+    gt = (est + rng.normal(0, 0.01, (B, V, 3)) + rng.normal(0, 0.05, (B, 1, 3))).astype(np.float32)
+    out = {}
+    for tag, name in (('aligned', 'translation'), ('raw', 'none')):
+        pe = mod.PointError(mod.build_alignment(name))
+        out[f'error_{tag}'] = np.asarray(pe(est.copy(), gt.copy()), np.float64)
+    np.savez_compressed(os.path.join(G, 'v2v.npz'), est=est, gt=gt, **out)
+    print('v2v.npz', os.path.getsize(os.path.join(G, 'v2v.npz')), 'bytes; mean aligned error', out['error_aligned'].mean())
+
+
+def p2p_fixture():
+    """Runs the reference's own v2vhdError (regressor/human_shape/utils/metrics.py:368-456, loaded by path behind stubs of
+    open3d / .np_utils / .typing) on seeded sparse point regressors (3 barycentric weights per point) and meshes, in
+    float64 on the CPU as the evaluator does (evaluation.py:258-260)."""
+    import pickle
+    import tempfile
+    import scipy.sparse as sp
+    mod = _load_ref_metrics()
     rng = np.random.default_rng(77)
     P, V1, V2, B = 700, 400, 250, 3
 
@@ -288,7 +313,7 @@ def p2p_fixture():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess', 'b2a', 'p2p']
+    which = sys.argv[1:] or ['body', 'smplx', 'head', 'hrnet', 'preprocess', 'b2a', 'p2p', 'v2v']
     torch.set_num_threads(8)
     if 'body' in which:
         body_fixture()
@@ -304,3 +329,5 @@ if __name__ == '__main__':
         b2a_fixture()
     if 'p2p' in which:
         p2p_fixture()
+    if 'v2v' in which:
+        v2v_fixture()
