@@ -534,20 +534,21 @@ extern "C" int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t 
     // ---- operands of the fused tcgen05 LBS kernel (smplx_lbs.cu)
     const int Vpad = (V + 127) / 128 * 128, KP = (J - 1) * 9, KPpad = (KP + 63) / 64 * 64;
     s.Vpad = Vpad; s.KPpad = KPpad;
-    std::vector<__half> bh((size_t)3 * Vpad * KPpad, __float2half_rn(0.f)), bl(bh.size(), __float2half_rn(0.f));
+    const int nKB = KPpad / 32;
+    std::vector<__half> pb((size_t)nKB * 3 * Vpad * 64, __float2half_rn(0.f));
     for (int k = 0; k < KP; ++k) {
       const float *row = d->posedirs + (size_t)k * V * 3;
+      const int kb = k / 32, kk = k % 32;
       for (int v = 0; v < V; ++v)
         for (int c = 0; c < 3; ++c) {
           const float x = row[(size_t)v * 3 + c] * kPoseScale;
           const __half h = __float2half_rn(x);
-          const size_t o = ((size_t)c * Vpad + v) * KPpad + k;
-          bh[o] = h;
-          bl[o] = __float2half_rn((x - __half2float(h)) * 2048.0f);
+          const size_t o = (((size_t)kb * 3 + c) * Vpad + v) * 64 + kk;
+          pb[o] = h;
+          pb[o + 32] = __float2half_rn((x - __half2float(h)) * 2048.0f);
         }
     }
-    s.pbasis_hi = upload(m, bh, err);
-    s.pbasis_lo = upload(m, bl, err);
+    s.pbasis = upload(m, pb, err);
     std::vector<float> sp((size_t)(NB + 1) * 3 * Vpad, 0.f);
     for (int v = 0; v < V; ++v)
       for (int c = 0; c < 3; ++c) {
@@ -557,11 +558,10 @@ extern "C" int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t 
     s.shape_planes = upload(m, sp, err);
     m->fused_ok = false;
     if (err == cudaSuccess && get_encode()) {
-      cuuint64_t dims[3] = {(cuuint64_t)KPpad, (cuuint64_t)Vpad, 3};
-      cuuint64_t strides[2] = {(cuuint64_t)KPpad * 2, (cuuint64_t)Vpad * KPpad * 2};
-      cuuint32_t box[3] = {32, 128, 3};
-      m->fused_ok = encode(&m->basis_map_hi, s.pbasis_hi, 3, dims, strides, box, 32) &&
-                    encode(&m->basis_map_lo, s.pbasis_lo, 3, dims, strides, box, 32);
+      cuuint64_t dims[4] = {64, (cuuint64_t)Vpad, 3, (cuuint64_t)nKB};
+      cuuint64_t strides[3] = {128, (cuuint64_t)Vpad * 128, (cuuint64_t)3 * Vpad * 128};
+      cuuint32_t box[4] = {64, 128, 3, 1};
+      m->fused_ok = encode(&m->basis_map, s.pbasis, 4, dims, strides, box, 64);
     }
   }
   if (err != cudaSuccess) {

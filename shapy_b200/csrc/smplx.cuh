@@ -30,7 +30,7 @@ struct SmplxDev {
   // ---- packed operands of the fused tcgen05 LBS kernel (smplx_lbs.cu)
   int Vpad;               /* V rounded up to a multiple of 128 */
   int KPpad;              /* (J-1)*9 rounded up to a multiple of 64 */
-  __half *pbasis_hi, *pbasis_lo; /* [3 planes][Vpad][KPpad] fp16, K-major: posedirs * kPoseScale as hi + lo / 2048 */
+  __half *pbasis;         /* [KPpad / 32 k-blocks][3 planes][Vpad][hi 32 | lo 32] fp16: posedirs * kPoseScale as hi + lo / 2048 */
   float *shape_planes;    /* [(NB + 1) * 3][Vpad]: row l*3+c = shapedirs coefficient l, coordinate c; rows NB*3+c = template */
 };
 
@@ -39,7 +39,7 @@ struct SmplxDev {
 struct shapy_smplx {
   shapy::SmplxDev d;
   std::vector<void *> allocs;
-  CUtensorMap basis_map_hi, basis_map_lo;   // (K, Vpad, 3) fp16, box (32, 128, 3), SWIZZLE_64B
+  CUtensorMap basis_map;                    // (64, Vpad, 3, KPpad / 32) fp16, box (64, 128, 3, 1), SWIZZLE_128B
   bool fused_ok = false;                    // the packed operands above exist and the maps encoded
 };
 

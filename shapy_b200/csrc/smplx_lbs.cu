@@ -11,8 +11,9 @@
 // and the only part that is not a stream: in fp32 SIMT it alone costs more than the HBM time of the whole kernel.  It
 // runs on the tensor cores as a split-fp16 GEMM (hi.hi + hi.lo + lo.hi, fp32 accumulate: ~22 mantissa bits, the same
 // scheme as the HRNet convolutions):
-//   A operand  pose basis P, re-laid out once at model load as [coordinate plane][vertex][k] fp16 hi/lo (K-major,
-//              scaled by 2^10 into fp16's normal range), streamed by TMA as SWIZZLE_64B k-blocks of 32
+//   A operand  pose basis P, re-laid out once at model load as [k-block][coordinate plane][vertex][hi 32 k | lo 32 k]
+//              fp16 (K-major, scaled by 2^10 into fp16's normal range): one contiguous 16 KB block per (k-block,
+//              plane, vertex tile), fetched by ONE TMA box per k-block into 128-byte SWIZZLE_128B rows
 //   B operand  pose features of a group of 32 bodies, written by the CTA itself into the swizzled K-major layout
 //   D          TMEM: lane = vertex (128 per tile), column = body; three planes (x, y, z) of [D0 | D1] per tile
 // so that in the epilogue a thread owns ONE vertex: its template / shape-basis / skinning-weight constants are loaded
@@ -23,7 +24,9 @@
 // group prologue (betas, pose features, kinematic chain: ~2 us of SIMT work) is paid once per group and CTA.
 // Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..17 prologue + epilogue.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "smplx.cuh"
 #include "umma.cuh"
@@ -38,20 +41,21 @@ constexpr int kLbsEpi = 16;        // prologue / epilogue warps (multiple of 4: 
 constexpr int kLbsThreads = 64 + 32 * kLbsEpi;
 constexpr int kLbsMaxKB = 8;       // k-blocks of the pose feature that fit next to everything else (n_rot <= 29)
 constexpr int kLbsNB = 10;         // shape coefficients held in registers
-constexpr uint32_t kPlaneBytes = LV * LKB * 2;            // 8 KB: one coordinate plane of a k-block, one part
-constexpr uint32_t kPartBytes = 3 * kPlaneBytes;          // 24 KB
-constexpr uint32_t kStageBytes = 2 * kPartBytes;          // hi + lo
+constexpr int kLbsPairs = (LG * kMaxJoints + 32 * kLbsEpi - 1) / (32 * kLbsEpi);   // (body, joint) pairs per prologue thread
+constexpr uint32_t kPlaneBytes = LV * 128;                // 16 KB: one coordinate plane of a k-block: 128 rows x [hi 64 B | lo 64 B]
+constexpr uint32_t kStageBytes = 3 * kPlaneBytes;         // 48 KB: one TMA box
 constexpr uint32_t kCoefBlkBytes = 2 * LG * LKB * 2;      // 4 KB: [C_hi rows | C_lo rows] of one k-block
 constexpr float kLoInvL = 1.0f / 2048.0f;
 
 struct alignas(64) LbsParams {
-  CUtensorMap basis_hi, basis_lo;
+  CUtensorMap basis;
   SmplxDev m;
   const float *betas, *rot;
   int n_rot, B, Kp, nkb, n_vt, n_items;
   float *vertices, *v_shaped, *joints;
   int *lut;
   uint32_t idesc64, idesc32;
+  long long *dbg;   // optional [gridDim.x][32] cycle stamps (SHAPY_LBS_DEBUG=1)
 };
 
 // byte offset of element (row r, k kk) inside a [rows][32 k] fp16 block laid out K-major with SWIZZLE_64B
@@ -90,6 +94,10 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   const uint32_t coef_full = acc_empty0 + 16u;
   const uint32_t tmem_slot = coef_full + 8u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // kinematic-tree tables (a few hundred bytes): read from shared memory inside the level loop
+  __shared__ int s_parents[kMaxJoints], s_level_joints[kMaxJoints], s_level_off[kMaxJoints + 1];
+  for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_parents[i] = m.parents[i]; s_level_joints[i] = m.level_joints[i]; }
+  for (int i = threadIdx.x; i <= m.n_levels; i += blockDim.x) s_level_off[i] = m.level_off[i];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -108,6 +116,8 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_launch_dependents();
   pdl_wait();
+  const long long c0 = clock64();
+  auto stamp = [&](int slot) { if (p.dbg) p.dbg[(size_t)blockIdx.x * 32 + slot] = clock64() - c0; };
 
   // contiguous item range of this CTA; item id = group * n_vt + vertex tile
   const int it_lo = (int)((long long)p.n_items * blockIdx.x / gridDim.x);
@@ -124,8 +134,7 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           mbar_wait(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), kStageBytes);
           const uint32_t sb = stage0 + s * kStageBytes;
-          tma_load_3d(sb, &p.basis_hi, full_bar(s), kb * LKB, vt * LV, 0);
-          tma_load_3d(sb + kPartBytes, &p.basis_lo, full_bar(s), kb * LKB, vt * LV, 0);
+          tma_load_4d(sb, &p.basis, full_bar(s), 0, vt * LV, 0, kb);
           if (++s == LStages) { s = 0; ph ^= 1; }
         }
       }
@@ -141,13 +150,15 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
         mbar_wait(coef_full, (uint32_t)(gchanges & 1));
         ++gchanges;
         gprev = g;
+        if (lane == 0 && lt == 0) stamp(16);
       }
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(acc_empty0 + 8u * buf, aph ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t dhi = desc_hi_swz<LKB>();
+        const uint32_t dhi = desc_hi_swz<LKB>();       // B operand: 64-byte rows, SWIZZLE_64B
+        const uint32_t ahi = desc_hi_swz<64>();        // A operand: 128-byte rows [hi | lo], SWIZZLE_128B
         const uint32_t dbase = tmem_base + buf * 256u;
         int s_l = s;
         uint32_t ph_l = ph;
@@ -163,14 +174,15 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
 #pragma unroll
             for (int ks = 0; ks < LKB / 16; ++ks) {
               // [D0 | D1] (+)= P_hi . [C_hi | C_lo]^T ; D1 += P_lo . C_hi^T
-              umma_f16_lh(d, ac + 2 * ks, dhi, b16 + 2 * ks, dhi, p.idesc64, (kb | ks) ? 1u : 0u);
-              umma_f16_lh(d + LG, ac + (kPartBytes >> 4) + 2 * ks, dhi, b16 + 2 * ks, dhi, p.idesc32, 1u);
+              umma_f16_lh(d, ac + 2 * ks, ahi, b16 + 2 * ks, dhi, p.idesc64, (kb | ks) ? 1u : 0u);
+              umma_f16_lh(d + LG, ac + 4 + 2 * ks, ahi, b16 + 2 * ks, dhi, p.idesc32, 1u);   // lo half of the row: +64 B
             }
           }
           umma_commit(empty_bar(s_l));
           if (++s_l == LStages) { s_l = 0; ph_l ^= 1; }
         }
         umma_commit(acc_full0 + 8u * buf);
+        if (lt < 2) stamp(17 + lt);
       }
       __syncwarp();
       for (int kb = 0; kb < p.nkb; ++kb) { if (++s == LStages) { s = 0; ph ^= 1; } }
@@ -193,50 +205,86 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           const int bl = i / 12, l = i % 12;
           betas_s[i] = (bl < nb && l < m.NB) ? p.betas[(size_t)(b0 + bl) * m.NB + l] : 0.f;
         }
-        // ---- pose features (R[1:] - I) as fp16 hi / lo rows of the B operand
-        for (int i = et; i < LG * p.nkb * LKB; i += 32 * kLbsEpi) {
-          const int bl = i / (p.nkb * LKB), k = i % (p.nkb * LKB);
-          float f = 0.f;
-          if (bl < nb && k < p.Kp) {
-            const int j = 1 + k / 9, e = k % 9;
-            f = p.rot[((size_t)(b0 + bl) * p.n_rot + j) * 9 + e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        // ---- pose features (R[1:] - I) as fp16 hi / lo rows of the B operand; four independent loads in flight per
+        // thread (a first version had one dependent L2 round trip per element)
+        {
+          const int total = LG * p.nkb * LKB, per_body = p.nkb * LKB;
+          for (int i0 = et; i0 < total; i0 += 4 * 32 * kLbsEpi) {
+            float f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u * 32 * kLbsEpi;
+              const int bl = i / per_body, k = i - bl * per_body;
+              f[u] = 0.f;
+              if (i < total && bl < nb && k < p.Kp) {
+                const int j = 1 + k / 9, e = k - (j - 1) * 9;
+                f[u] = __ldg(p.rot + ((size_t)(b0 + bl) * p.n_rot + j) * 9 + e) - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u * 32 * kLbsEpi;
+              if (i >= total) break;
+              const int bl = i / per_body, k = i - bl * per_body;
+              const __half h = __float2half_rn(f[u]);
+              const __half l = __float2half_rn((f[u] - __half2float(h)) * 2048.0f);
+              uint8_t *blk = smem_gen + (coef0 - smem_base) + (k / LKB) * kCoefBlkBytes;
+              *reinterpret_cast<__half *>(blk + sw64_off(bl, k % LKB)) = h;
+              *reinterpret_cast<__half *>(blk + sw64_off(LG + bl, k % LKB)) = l;
+            }
           }
-          const __half h = __float2half_rn(f);
-          const __half l = __float2half_rn((f - __half2float(h)) * 2048.0f);
-          uint8_t *blk = smem_gen + (coef0 - smem_base) + (k / LKB) * kCoefBlkBytes;
-          *reinterpret_cast<__half *>(blk + sw64_off(bl, k % LKB)) = h;
-          *reinterpret_cast<__half *>(blk + sw64_off(LG + bl, k % LKB)) = l;
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(coef_full);
-        // ---- kinematic chain, level by level, one thread per (body, joint); only A is kept:
+        if (et == 0 && lt == 0) stamp(1);
+        // ---- kinematic chain, level by level; only A is kept:
         //   A_c.R = A_p.R R_c ;  A_c.t = A_p.R J_c + A_p.t - A_c.R J_c   (== G_c - [0 | G_c.R J_c] of lbs.py:279-293,
         //   since G_c.t = G_p.R (J_c - J_p) + G_p.t and A_p.t = G_p.t - G_p.R J_p)
+        // Thread et owns the (body, joint) pairs et, et + 512, ... in LEVEL order (pair id = level-ordered joint slot
+        // * 32 + body), at most kLbsPairs of them.  Everything a pair needs from global memory -- its rotation and its
+        // rest joint J = J_template + J_dirs . beta -- is loaded / computed into registers BEFORE the level loop, with
+        // all loads in flight at once; the level loop itself only touches shared memory.  (A first version loaded
+        // J_dirs and the rotation inside the level loop: ten levels of serialised L2 latency, 70 us per group.)
         epi_bar();                       // betas_s visible
+        float Rp[kLbsPairs][9], Jp[kLbsPairs][3];
+#pragma unroll
+        for (int k = 0; k < kLbsPairs; ++k) {
+          const int id = et + k * 32 * kLbsEpi;
+          const int bl = id % LG, slot = id / LG;
+          const bool on = slot < J && bl < nb;
+          const int j = on ? s_level_joints[slot] : 0;
+          if (on && j < p.n_rot) {
+            const float *rp = p.rot + ((size_t)(b0 + bl) * p.n_rot + j) * 9;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Rp[k][e] = __ldg(rp + e);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Rp[k][e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
+          }
+          const float *bt = betas_s + bl * 12;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float *jd = m.J_dirs + (size_t)(j * 3 + c) * m.NC;
+            float jv[kLbsNB];
+#pragma unroll
+            for (int l = 0; l < kLbsNB; ++l) jv[l] = on ? __ldg(jd + l) : 0.f;
+            float sacc = on ? __ldg(m.J_template + j * 3 + c) : 0.f;
+#pragma unroll
+            for (int l = 0; l < kLbsNB; ++l) sacc += jv[l] * bt[l];
+            Jp[k][c] = sacc;
+          }
+        }
+        if (et == 0 && lt == 0) stamp(2);
         for (int lv = 0; lv < m.n_levels; ++lv) {
-          const int off = m.level_off[lv], cnt = m.level_off[lv + 1] - off;
-          for (int i = et; i < cnt * LG; i += 32 * kLbsEpi) {
-            const int bl = i % LG, j = m.level_joints[off + i / LG];
-            if (bl >= nb) continue;
-            const float *bt = betas_s + bl * 12;
-            float Jc[3];
+          const int off = s_level_off[lv], end = s_level_off[lv + 1];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float *jd = m.J_dirs + (size_t)(j * 3 + c) * m.NC;
-              float sacc = m.J_template[j * 3 + c];
-              for (int l = 0; l < m.NB; ++l) sacc += jd[l] * bt[l];
-              Jc[c] = sacc;
-            }
-            float R[9];
-            if (j < p.n_rot) {
-              const float *rp = p.rot + ((size_t)(b0 + bl) * p.n_rot + j) * 9;
-#pragma unroll
-              for (int e = 0; e < 9; ++e) R[e] = rp[e];
-            } else {
-#pragma unroll
-              for (int e = 0; e < 9; ++e) R[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
-            }
+          for (int k = 0; k < kLbsPairs; ++k) {
+            const int id = et + k * 32 * kLbsEpi;
+            const int bl = id % LG, slot = id / LG;
+            if (slot < off || slot >= end || bl >= nb) continue;
+            const int j = s_level_joints[slot];
+            const float *R = Rp[k], *Jc = Jp[k];
             float *Ao = Aj + ((size_t)bl * J + j) * 12;
             if (lv == 0) {
 #pragma unroll
@@ -245,7 +293,7 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
                 Ao[r * 4 + 3] = Jc[r] - (R[r * 3] * Jc[0] + R[r * 3 + 1] * Jc[1] + R[r * 3 + 2] * Jc[2]);
               }
             } else {
-              const float *Ap = Aj + ((size_t)bl * J + m.parents[j]) * 12;
+              const float *Ap = Aj + ((size_t)bl * J + s_parents[j]) * 12;
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
                 const float g0 = Ap[r * 4], g1 = Ap[r * 4 + 1], g2 = Ap[r * 4 + 2], gt = Ap[r * 4 + 3];
@@ -266,6 +314,7 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           }
           epi_bar();
         }
+        if (et == 0 && lt == 0) stamp(3);
         // ---- dynamic-contour LUT row (lbs.py:30-41, rotation_utils.py:86-92), once per group
         if (vt == 0 && m.D > 0 && p.lut && et < nb) {
           float rel[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -300,9 +349,20 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
       for (int l = 0; l < kLbsNB; ++l)
 #pragma unroll
         for (int c = 0; c < 3; ++c) S[l][c] = m.shape_planes[(size_t)(l * 3 + c) * m.Vpad + vc];
+      // skinning weights of this vertex: the first four ELL slots live in registers for the whole group
+      float ew[4];
+      int ej[4];
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const bool on = vok && sl < m.ell_w_n;
+        ew[sl] = on ? __ldg(m.ell_w + (size_t)sl * m.V + v) : 0.f;
+        ej[sl] = on ? __ldg(m.ell_idx + (size_t)sl * m.V + v) : 0;
+      }
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
+      if (et == 0 && lt < 2) stamp(4 + 3 * lt);
       mbar_wait(acc_full0 + 8u * buf, aph);
+      if (et == 0 && lt < 2) stamp(5 + 3 * lt);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16) + part * 8;
       const int rows_here = min(32, m.V - v0w);      // > 0 for every tile (V > (n_vt - 1) * 128 + 96 is NOT assumed)
@@ -342,9 +402,9 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           float o3[3] = {0.f, 0.f, 0.f};
           if (vok) {
             for (int sl = 0; sl < m.ell_w_n; ++sl) {
-              const float w = m.ell_w[(size_t)sl * m.V + v];
+              const float w = sl < 4 ? (sl == 0 ? ew[0] : (sl == 1 ? ew[1] : (sl == 2 ? ew[2] : ew[3]))) : m.ell_w[(size_t)sl * m.V + v];
               if (w == 0.f) continue;
-              const int j = m.ell_idx[(size_t)sl * m.V + v];
+              const int j = sl < 4 ? (sl == 0 ? ej[0] : (sl == 1 ? ej[1] : (sl == 2 ? ej[2] : ej[3]))) : m.ell_idx[(size_t)sl * m.V + v];
               const float4 *Ab = reinterpret_cast<const float4 *>(Aj + ((size_t)bl * J + j) * 12);
               const float4 r0 = Ab[0], r1 = Ab[1], r2 = Ab[2];
               o3[0] += w * (r0.x * vp[0] + r0.y * vp[1] + r0.z * vp[2] + r0.w);
@@ -381,10 +441,12 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           }
         }
       }
+      if (et == 0 && lt < 2) stamp(6 + 3 * lt);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(31);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -392,20 +454,20 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
 
 size_t lbs_smem_bytes(int J) {
   return 1024 + LStages * kStageBytes + kLbsMaxKB * kCoefBlkBytes + (size_t)LG * J * 12 * 4 + LG * 12 * 4 +
-         kLbsEpi * 2 * 100 * 4 + 16 + 128;
+         kLbsEpi * 2 * 100 * 4 + 16 + 128;   // + 1 KB of static tables (s_parents ...): 232 080 of the 232 448 bytes
 }
 
 int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot, int n_rot, int B, float *vertices,
                      float *v_shaped, float *joints, int *lut, cudaStream_t st) {
   const SmplxDev &d = mm->d;
   const int Kp = (n_rot - 1) * 9, nkb = std::max(1, ceil_div(Kp, LKB));
-  if (!mm->fused_ok || !vertices || d.NB != kLbsNB || nkb > kLbsMaxKB || lbs_smem_bytes(d.J) > 227 * 1024)
+  if (!mm->fused_ok || !vertices || d.NB != kLbsNB || nkb > kLbsMaxKB || lbs_smem_bytes(d.J) > 226 * 1024)
     return SHAPY_ERR_UNSUPPORTED;
   static const bool off = []() { const char *e = getenv("SHAPY_LBS_FUSED"); return e && e[0] == '0'; }();
   if (off) return SHAPY_ERR_UNSUPPORTED;
   LbsParams p;
   memset(&p, 0, sizeof(p));
-  p.basis_hi = mm->basis_map_hi; p.basis_lo = mm->basis_map_lo;
+  p.basis = mm->basis_map;
   p.m = d;
   p.betas = betas; p.rot = rot; p.n_rot = n_rot; p.B = B; p.Kp = Kp; p.nkb = nkb;
   p.n_vt = d.Vpad / LV;
@@ -414,7 +476,7 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
   p.idesc64 = (1u << 4) | ((uint32_t)((2 * LG) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.idesc32 = (1u << 4) | ((uint32_t)(LG >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static std::atomic<unsigned long long> attr_done{0};
-  SHAPY_CUDA_TRY(set_max_dynamic_smem(smplx_lbs_kernel, 227 * 1024, attr_done));
+  SHAPY_CUDA_TRY(set_max_dynamic_smem(smplx_lbs_kernel, 226 * 1024, attr_done));   // + 1 KB static <= 227 KB
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -425,6 +487,30 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
   cfg.blockDim = dim3(kLbsThreads);
   cfg.dynamicSmemBytes = lbs_smem_bytes(d.J);
   cfg.stream = st;
+  static const bool dbg = getenv("SHAPY_LBS_DEBUG") != nullptr;
+  if (dbg) {   // synchronous: per-CTA cycle stamps of the roles (prologue / MMA / epilogue phases)
+    long long *d = nullptr;
+    cudaMalloc(&d, (size_t)grid * 32 * 8);
+    cudaMemset(d, 0, (size_t)grid * 32 * 8);
+    p.dbg = d;
+    SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel, p));
+    cudaStreamSynchronize(st);
+    std::vector<long long> h((size_t)grid * 32);
+    cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    const char *names[32] = {"", "coef_ready", "pairs_loaded", "chain_done", "it0_consts", "it0_acc_full", "it0_epi_done",
+                             "it1_consts", "it1_acc_full", "it1_epi_done", "", "", "", "", "", "", "mma_coef_wait",
+                             "mma_it0_issued", "mma_it1_issued", "", "", "", "", "", "", "", "", "", "", "", "", "exit"};
+    fprintf(stderr, "[lbs] B %d items %d grid %d: cycles since kernel entry (avg / max over CTAs that reached the point)\n", B, p.n_items, grid);
+    for (int k = 0; k < 32; ++k) {
+      if (!names[k][0]) continue;
+      double sum = 0; long long mx = 0; int n = 0;
+      for (int c = 0; c < grid; ++c) { long long v = h[(size_t)c * 32 + k]; if (v > 0) { sum += v; mx = std::max(mx, v); ++n; } }
+      if (n) fprintf(stderr, "[lbs]   %-16s avg %8.0f max %8lld (n=%d)\n", names[k], sum / n, mx, n);
+    }
+    count_launch();
+    return SHAPY_OK;
+  }
   SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel, p));
   count_launch();
   return SHAPY_OK;

@@ -38,6 +38,20 @@ class HostPipeline:
         self.n = 0
         self.last_out = torch.cuda.Event()
 
+    def _new_slot(self, shape, dtype, cur):
+        """Device staging buffer of the copy-in stream.  The caching allocator hands out memory that is free in the
+        ALLOCATING stream's order: a block released by Python while the compute stream still has kernels pending on
+        it (an intermediate of the previous batch) is legal for a new compute-stream tensor, but not for a buffer that
+        the copy-in stream writes right away.  (Found the hard way: the descriptor table of batch 1 landed in a block
+        batch 0's head kernel was still writing, and the crop kernel then read garbage offsets.)  So the buffer is
+        allocated under the copy-in stream, that stream first catches up with the compute stream, and the buffer's use
+        by the compute stream is recorded so that a later free waits for it."""
+        self.s_in.wait_stream(cur)
+        with torch.cuda.stream(self.s_in):
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+        t.record_stream(cur)
+        return t
+
     def submit(self, images_host: torch.Tensor, out_host: Dict[str, torch.Tensor],
                between: Optional[Callable[[], None]] = None):
         """Enqueues one batch: pinned host images in, pinned host result tensors out (filled asynchronously; call
@@ -47,7 +61,7 @@ class HostPipeline:
         cur = torch.cuda.current_stream(self.device)
         slot = self.n % self.depth
         if self.slots[slot] is None or self.slots[slot].shape != images_host.shape:
-            self.slots[slot] = torch.empty(images_host.shape, dtype=images_host.dtype, device=self.device)
+            self.slots[slot] = self._new_slot(images_host.shape, images_host.dtype, cur)
         with torch.cuda.stream(self.s_in):
             if self.n >= self.depth:
                 self.s_in.wait_event(self.slot_free[slot])        # the forward that last read this slot is done
@@ -84,9 +98,9 @@ class HostPipeline:
         cur = torch.cuda.current_stream(self.device)
         slot = self.n % self.depth
         if self.u8_slots[slot] is None or self.u8_slots[slot].numel() != images_u8_host.numel():
-            self.u8_slots[slot] = torch.empty(images_u8_host.numel(), dtype=torch.uint8, device=self.device)
+            self.u8_slots[slot] = self._new_slot((images_u8_host.numel(),), torch.uint8, cur)
         if self.desc_slots[slot] is None or self.desc_slots[slot].numel() != desc_host.numel():
-            self.desc_slots[slot] = torch.empty(desc_host.numel(), dtype=torch.uint8, device=self.device)
+            self.desc_slots[slot] = self._new_slot((desc_host.numel(),), torch.uint8, cur)
         with torch.cuda.stream(self.s_in):
             if self.n >= self.depth:
                 self.s_in.wait_event(self.slot_free[slot])

@@ -153,23 +153,43 @@ def test_mmi_op_random_meshes(data, Q, F, M):
 
 def test_config4_4096_random_beta_bodies_vs_oracle(data):
     """BASELINE configs[3]: 4 096 clipped-normal betas (seed 3) -> T-pose bodies -> measurements in one launch each;
-    64 of the 4 096 rows against the CPU oracle (shape blend restated in numpy, measure_oracle)."""
+    64 of the 4 096 rows against the CPU oracle (shape blend restated in numpy, measure_oracle).
+
+    The synthetic shape basis is white noise per vertex, so a few per cent of these bodies are crumpled enough that a
+    slicing plane cuts > 1 024 triangles.  That is outside the reference's own domain (its buffers hold 256 collisions
+    per query triangle, beyond which mesh_mesh_intersect_cuda_op.cu:551-557 writes out of bounds); the kernel must
+    then report NaN + status instead of a truncated circumference.  Every plane with <= 1 024 points must match the
+    oracle (run with a capacity large enough never to truncate)."""
     g, lm, ops = data
     smplx = synth.make_smplx()
     packed = ops.SmplxModel(dict(smplx), 'cuda')
     betas = torch.randn(4096, 10, generator=torch.Generator().manual_seed(3)).clamp(-3, 3)
     vs = ops.smplx_forward_shape(packed, betas.cuda())
     faces = smplx['faces_tensor'].to(torch.int32).cuda()
-    out, _, _, status = ops.measure(ops.make_landmarks(lm), v_shaped=vs, faces_i32=faces, return_points=True)
-    assert int(status.item()) == 0
-    out = out.cpu().numpy()
-    rows = np.random.default_rng(5).choice(4096, 64, replace=False)
+    out, _, cnt, status = ops.measure(ops.make_landmarks(lm), v_shaped=vs, faces_i32=faces, return_points=True, max_points=1024)
+    out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+    n_bad = int(np.isnan(out).any(1).sum())
+    assert (int(status.item()) != 0) == (n_bad > 0)
+    assert n_bad < 0.05 * 4096, n_bad
+    assert not np.isnan(out[:, :2]).any()                                      # mass / height never overflow
+    rows = list(np.random.default_rng(5).choice(4096, 60, replace=False)) + list(np.nonzero(np.isnan(out).any(1))[0][:4])
     vt = smplx['v_template'].double().numpy()
     S = smplx['shapedirs'].double().numpy()                                    # (V, 3, 10)
     f = smplx['faces_tensor'].numpy()
+    checked = 0
     for r in rows:
         ref_v = (vt + S @ betas[r].double().numpy()).astype(np.float32)
         assert np.abs(vs[r].cpu().numpy() - ref_v).max() < 2e-6
-        ref = measure_oracle.measure(ref_v, f, lm)
-        for i, name in enumerate(('mass', 'height', 'chest', 'waist', 'hips')):
-            assert abs(out[r, i] - ref[name]) / abs(ref[name]) < 1e-4, (int(r), name, out[r, i], ref[name])
+        tris = np.ascontiguousarray(ref_v[f])
+        assert abs(out[r, 0] - measure_oracle.mass(tris)) / measure_oracle.mass(tris) < 1e-4
+        assert abs(out[r, 1] - measure_oracle.height(tris, lm)) / measure_oracle.height(tris, lm) < 1e-4
+        for i, name in enumerate(('chest', 'waist', 'hips')):
+            val, pts, _ = measure_oracle.periphery(tris, lm[name]['face_idx'], lm[name]['bc'], max_collisions=4096)
+            n = len(pts) // 2                                                   # the oracle stores each point twice
+            if n > 1024:
+                assert np.isnan(out[r, 2 + i]), (int(r), name, n, out[r, 2 + i])
+            else:
+                assert cnt[r, i] == n, (int(r), name, cnt[r, i], n)
+                assert abs(out[r, 2 + i] - val) / abs(val) < 1e-4, (int(r), name, out[r, 2 + i], val)
+                checked += 1
+    assert checked > 150
