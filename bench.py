@@ -92,8 +92,10 @@ class ClockSampler:
 
 def conv_traffic(batch: int, mode: int):
     """DRAM bytes (read + write) of all conv launches of one HRNet forward, from the committed ncu capture
-    profiles/r01_traffic.json (taken at B=64, split mode); None for any other configuration."""
-    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    profiles/r02_traffic.json (r01 if absent; taken at B=64, split mode); None for any other configuration."""
+    path = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     if batch != 64 or mode != 1 or not os.path.exists(path):
         return None
     with open(path) as f:

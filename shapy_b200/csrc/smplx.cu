@@ -270,7 +270,7 @@ struct JointsArgs {
   float *joints, *proj;
 };
 
-__global__ void __launch_bounds__(128) smplx_joints_kernel(JointsArgs a) {
+__global__ void __launch_bounds__(512) smplx_joints_kernel(JointsArgs a) {
   // launched as a programmatic dependent of the kernel that writes the vertices: its launch latency overlaps that
   // kernel's tail; everything below reads the predecessor's output, so wait for its completion first
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -644,7 +644,7 @@ extern "C" int shapy_smplx_forward(const shapy_smplx_t *m, const float *betas, c
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(B);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(512);     // 16 warps: the 14 sparse J14 rows and the 68 landmarks are each one pass of dependent loads
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

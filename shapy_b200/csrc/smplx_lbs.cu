@@ -39,7 +39,7 @@ constexpr int LKB = 32;            // k per block: 64-byte rows, SWIZZLE_64B
 constexpr int LStages = 2;
 constexpr int kLbsEpi = 16;        // prologue / epilogue warps (multiple of 4: TMEM lane-quarter rule)
 constexpr int kLbsThreads = 64 + 32 * kLbsEpi;
-constexpr int kLbsMaxKB = 8;       // k-blocks of the pose feature that fit next to everything else (n_rot <= 29)
+constexpr int kLbsMaxKB = 6;       // k-blocks of the pose feature that fit next to everything else (n_rot <= 22: SHAPY)
 constexpr int kLbsNB = 10;         // shape coefficients held in registers
 constexpr int kLbsPairs = (LG * kMaxJoints + 32 * kLbsEpi - 1) / (32 * kLbsEpi);   // (body, joint) pairs per prologue thread
 constexpr uint32_t kPlaneBytes = LV * 128;                // 16 KB: one coordinate plane of a k-block: 128 rows x [hi 64 B | lo 64 B]
@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   float *betas_s = reinterpret_cast<float *>(smem_gen + betas_off);                // [LG][12]
   const uint32_t rowst_off = betas_off + LG * 12 * 4;
   float *rowst = reinterpret_cast<float *>(smem_gen + rowst_off);                  // [kLbsEpi][2][100]
-  const uint32_t bar_base = smem_base + ((rowst_off + kLbsEpi * 2 * 100 * 4 + 15u) & ~15u);
+  const uint32_t jtab_off = rowst_off + kLbsEpi * 2 * 100 * 4;
+  float *jtab = reinterpret_cast<float *>(smem_gen + jtab_off);                    // [J * 3][12]: J_dirs[:, :NB] | J_template
+  const uint32_t bar_base = smem_base + ((jtab_off + (uint32_t)(m.J * 3 * 12 * 4) + 15u) & ~15u);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (LStages + s); };
   const uint32_t acc_full0 = bar_base + 16u * LStages;   // [2]
@@ -98,6 +100,10 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   __shared__ int s_parents[kMaxJoints], s_level_joints[kMaxJoints], s_level_off[kMaxJoints + 1];
   for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_parents[i] = m.parents[i]; s_level_joints[i] = m.level_joints[i]; }
   for (int i = threadIdx.x; i <= m.n_levels; i += blockDim.x) s_level_off[i] = m.level_off[i];
+  for (int i = threadIdx.x; i < m.J * 3 * 12; i += blockDim.x) {
+    const int r = i / 12, l = i % 12;
+    jtab[i] = l < m.NB ? m.J_dirs[(size_t)r * m.NC + l] : (l == m.NB ? m.J_template[r] : 0.f);
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -200,38 +206,34 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
       if (g != gprev) {
         gprev = g;
         epi_bar();                       // every warp is done with the previous group's A_j / betas
-        // ---- betas
+        // ---- betas and rotations of the group -> shared memory, coalesced (the rotations of 32 bodies are one
+        // contiguous range; they are staged in the A_j region, which is not written before the level loop below)
+        float *rs = Aj;                                  // [nb][n_rot * 9]
+        const int rper = p.n_rot * 9;
         for (int i = et; i < LG * 12; i += 32 * kLbsEpi) {
           const int bl = i / 12, l = i % 12;
-          betas_s[i] = (bl < nb && l < m.NB) ? p.betas[(size_t)(b0 + bl) * m.NB + l] : 0.f;
+          betas_s[i] = (bl < nb && l < m.NB) ? __ldg(p.betas + (size_t)(b0 + bl) * m.NB + l) : 0.f;
         }
-        // ---- pose features (R[1:] - I) as fp16 hi / lo rows of the B operand; four independent loads in flight per
-        // thread (a first version had one dependent L2 round trip per element)
         {
-          const int total = LG * p.nkb * LKB, per_body = p.nkb * LKB;
-          for (int i0 = et; i0 < total; i0 += 4 * 32 * kLbsEpi) {
-            float f[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u * 32 * kLbsEpi;
-              const int bl = i / per_body, k = i - bl * per_body;
-              f[u] = 0.f;
-              if (i < total && bl < nb && k < p.Kp) {
-                const int j = 1 + k / 9, e = k - (j - 1) * 9;
-                f[u] = __ldg(p.rot + ((size_t)(b0 + bl) * p.n_rot + j) * 9 + e) - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
-              }
+          const float *src = p.rot + (size_t)b0 * rper;
+          for (int i = et; i < nb * rper; i += 32 * kLbsEpi) rs[i] = __ldg(src + i);
+        }
+        epi_bar();
+        // ---- pose features (R[1:] - I) as fp16 hi / lo rows of the B operand
+        {
+          const int per_body = p.nkb * LKB;
+          for (int i = et; i < LG * per_body; i += 32 * kLbsEpi) {
+            const int bl = i / per_body, k = i - bl * per_body;
+            float f = 0.f;
+            if (bl < nb && k < p.Kp) {
+              const int e = k % 9;
+              f = rs[bl * rper + 9 + k] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u * 32 * kLbsEpi;
-              if (i >= total) break;
-              const int bl = i / per_body, k = i - bl * per_body;
-              const __half h = __float2half_rn(f[u]);
-              const __half l = __float2half_rn((f[u] - __half2float(h)) * 2048.0f);
-              uint8_t *blk = smem_gen + (coef0 - smem_base) + (k / LKB) * kCoefBlkBytes;
-              *reinterpret_cast<__half *>(blk + sw64_off(bl, k % LKB)) = h;
-              *reinterpret_cast<__half *>(blk + sw64_off(LG + bl, k % LKB)) = l;
-            }
+            const __half h = __float2half_rn(f);
+            const __half l = __float2half_rn((f - __half2float(h)) * 2048.0f);
+            uint8_t *blk = smem_gen + (coef0 - smem_base) + (k / LKB) * kCoefBlkBytes;
+            *reinterpret_cast<__half *>(blk + sw64_off(bl, k % LKB)) = h;
+            *reinterpret_cast<__half *>(blk + sw64_off(LG + bl, k % LKB)) = l;
           }
         }
         fence_proxy_async_smem();
@@ -242,11 +244,11 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
         //   A_c.R = A_p.R R_c ;  A_c.t = A_p.R J_c + A_p.t - A_c.R J_c   (== G_c - [0 | G_c.R J_c] of lbs.py:279-293,
         //   since G_c.t = G_p.R (J_c - J_p) + G_p.t and A_p.t = G_p.t - G_p.R J_p)
         // Thread et owns the (body, joint) pairs et, et + 512, ... in LEVEL order (pair id = level-ordered joint slot
-        // * 32 + body), at most kLbsPairs of them.  Everything a pair needs from global memory -- its rotation and its
-        // rest joint J = J_template + J_dirs . beta -- is loaded / computed into registers BEFORE the level loop, with
-        // all loads in flight at once; the level loop itself only touches shared memory.  (A first version loaded
-        // J_dirs and the rotation inside the level loop: ten levels of serialised L2 latency, 70 us per group.)
-        epi_bar();                       // betas_s visible
+        // * 32 + body), at most kLbsPairs of them.  A pair's rotation and rest joint J = J_template + J_dirs . beta
+        // are read from shared memory into registers BEFORE the level loop (which overwrites the staged rotations with
+        // A_j).  (A first version read J_dirs and the rotations from global memory inside the level loop: ten levels
+        // of serialised L2 latency, 70 us per group; a second one preloaded them from global memory with one sector
+        // per lane and was bound by the load unit.)
         float Rp[kLbsPairs][9], Jp[kLbsPairs][3];
 #pragma unroll
         for (int k = 0; k < kLbsPairs; ++k) {
@@ -254,27 +256,39 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           const int bl = id % LG, slot = id / LG;
           const bool on = slot < J && bl < nb;
           const int j = on ? s_level_joints[slot] : 0;
-          if (on && j < p.n_rot) {
-            const float *rp = p.rot + ((size_t)(b0 + bl) * p.n_rot + j) * 9;
 #pragma unroll
-            for (int e = 0; e < 9; ++e) Rp[k][e] = __ldg(rp + e);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 9; ++e) Rp[k][e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
-          }
+          for (int e = 0; e < 9; ++e)
+            Rp[k][e] = (on && j < p.n_rot) ? rs[bl * rper + j * 9 + e] : ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
           const float *bt = betas_s + bl * 12;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float *jd = m.J_dirs + (size_t)(j * 3 + c) * m.NC;
-            float jv[kLbsNB];
+            const float *jd = jtab + (j * 3 + c) * 12;
+            float sacc = jd[kLbsNB];
 #pragma unroll
-            for (int l = 0; l < kLbsNB; ++l) jv[l] = on ? __ldg(jd + l) : 0.f;
-            float sacc = on ? __ldg(m.J_template + j * 3 + c) : 0.f;
-#pragma unroll
-            for (int l = 0; l < kLbsNB; ++l) sacc += jv[l] * bt[l];
+            for (int l = 0; l < kLbsNB; ++l) sacc += jd[l] * bt[l];
             Jp[k][c] = sacc;
           }
         }
+        // dynamic-contour LUT row (lbs.py:30-41, rotation_utils.py:86-92), once per group, from the staged rotations
+        if (vt == 0 && m.D > 0 && p.lut && et < nb) {
+          float rel[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+          for (int qn = 0; qn < m.n_chain; ++qn) {
+            const int j = m.neck[qn];
+            float Rq[9];
+            for (int e = 0; e < 9; ++e) Rq[e] = j < p.n_rot ? rs[et * rper + j * 9 + e] : ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+            float o[9];
+            for (int r = 0; r < 3; ++r)
+              for (int c = 0; c < 3; ++c) o[r * 3 + c] = Rq[r * 3] * rel[c] + Rq[r * 3 + 1] * rel[3 + c] + Rq[r * 3 + 2] * rel[6 + c];
+            for (int e = 0; e < 9; ++e) rel[e] = o[e];
+          }
+          const float sy = sqrtf(rel[0] * rel[0] + rel[3] * rel[3]);
+          const float ang = atan2f(-rel[6], sy);
+          const float deg = fminf(-ang * 180.0f / 3.14159265358979323846f, 39.0f);
+          const int y = (int)rintf(deg);
+          const int row = y < 0 ? (y < -39 ? 78 : 39 - y) : y;
+          p.lut[b0 + et] = min(max(row, 0), m.rows - 1);
+        }
+        epi_bar();                       // every thread has its rotations in registers: the A_j region may be written
         if (et == 0 && lt == 0) stamp(2);
         for (int lv = 0; lv < m.n_levels; ++lv) {
           const int off = s_level_off[lv], end = s_level_off[lv + 1];
@@ -315,26 +329,6 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           epi_bar();
         }
         if (et == 0 && lt == 0) stamp(3);
-        // ---- dynamic-contour LUT row (lbs.py:30-41, rotation_utils.py:86-92), once per group
-        if (vt == 0 && m.D > 0 && p.lut && et < nb) {
-          float rel[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-          for (int qn = 0; qn < m.n_chain; ++qn) {
-            const int j = m.neck[qn];
-            float Rq[9];
-            for (int e = 0; e < 9; ++e)
-              Rq[e] = j < p.n_rot ? p.rot[((size_t)(b0 + et) * p.n_rot + j) * 9 + e] : ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
-            float o[9];
-            for (int r = 0; r < 3; ++r)
-              for (int c = 0; c < 3; ++c) o[r * 3 + c] = Rq[r * 3] * rel[c] + Rq[r * 3 + 1] * rel[3 + c] + Rq[r * 3 + 2] * rel[6 + c];
-            for (int e = 0; e < 9; ++e) rel[e] = o[e];
-          }
-          const float sy = sqrtf(rel[0] * rel[0] + rel[3] * rel[3]);
-          const float ang = atan2f(-rel[6], sy);
-          const float deg = fminf(-ang * 180.0f / 3.14159265358979323846f, 39.0f);
-          const int y = (int)rintf(deg);
-          const int row = y < 0 ? (y < -39 ? 78 : 39 - y) : y;
-          p.lut[b0 + et] = min(max(row, 0), m.rows - 1);
-        }
       }
       // ================================================================= epilogue of this item
       const int v0w = vt * LV + q * 32;            // first vertex of this warp's lane quarter
@@ -454,7 +448,7 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
 
 size_t lbs_smem_bytes(int J) {
   return 1024 + LStages * kStageBytes + kLbsMaxKB * kCoefBlkBytes + (size_t)LG * J * 12 * 4 + LG * 12 * 4 +
-         kLbsEpi * 2 * 100 * 4 + 16 + 128;   // + 1 KB of static tables (s_parents ...): 232 080 of the 232 448 bytes
+         kLbsEpi * 2 * 100 * 4 + (size_t)J * 3 * 12 * 4 + 16 + 128;   // + 1 KB of static tables (s_parents ...)
 }
 
 int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot, int n_rot, int B, float *vertices,
