@@ -139,14 +139,17 @@ def run_reference(args):
     model = synth.build_synthetic_regressor()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     smplx, lm = synth.make_smplx(), synth.load_landmarks()
-    # calibrate on one body (this is also the warm-up), then size the per-step sample so that the K timed
-    # steps take about two minutes in total
+    # One warm-up pass over the sample, then K timed passes.  The sample is `--ref-sample` bodies (8, the same as the
+    # in-line cpu_baseline leg of the GPU arm): the oneDNN / ATen convolutions of this port run at their best per-body
+    # rate there (21-25 bodies/s on the 16 host cores; 64 bodies per pass: 9.7 bodies/s, profiles/
+    # r02_bench_reference_arm_sample64.json), shrunk only if K passes would not fit in two minutes.
     x1 = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(0))
     t0 = time.perf_counter()
     cpu_reference_step(sd, smplx, lm, x1)
     t1 = time.perf_counter() - t0
-    sample = int(max(1, min(args.batch, 120.0 / max(args.steps, 1) / max(t1, 1e-3))))
+    sample = int(max(1, min(args.batch, args.ref_sample, 120.0 / max(args.steps, 1) / max(t1, 1e-3))))
     x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    cpu_reference_step(sd, smplx, lm, x)                                     # warm-up pass at the timed sample size
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_reference_step(sd, smplx, lm, x)
@@ -158,7 +161,7 @@ def run_reference(args):
             'config': {'workload': 'configs[2]: full SHAPY_A regressor, 224x224, CPU port of the reference path '
                                    '(oracle/: the same ATen / oneDNN kernels the reference modules call)',
                        'sample': f'{sample} bodies per step (per-body rate of the same workload; the GPU arm runs 64 per '
-                                 f'step), 1 warm-up pass of 1 body'},
+                                 f'step), 1 warm-up pass'},
             'cpu_baseline': {'value': v, 'unit': 'bodies/s', 'cores': cores, 'kind': 'port',
                              'sample': f'{sample} images per step x {args.steps} steps (HRNet+head+SMPL-X+measurements)'},
             'e2e': {'value': v, 'unit': 'bodies/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
