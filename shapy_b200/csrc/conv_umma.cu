@@ -61,6 +61,7 @@ struct alignas(64) UmmaParams {
   int G;                         // k-blocks per pipeline stage
   int stages;
   int relu;
+  int pdl_late;                  // 1: release the programmatic dependents when this CTA starts its LAST tile, not at entry
   int vec32;                     // out / residual rows are 32-byte aligned: 256-bit epilogue accesses
   uint32_t idesc, idesc2;        // idesc: N = NT;  idesc2: N = 2 NT ([B_hi | B_lo] in one MMA, split mode)
   uint32_t tmem_cols;
@@ -117,7 +118,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_launch_dependents();   // let the next launch start its prologue
+  // Programmatic dependent launch: the next kernel of this stream may start its prologue once every CTA here has
+  // released it.  Released at entry, its CTAs occupy SMs (which another lane's kernel could use) for this kernel's whole
+  // duration; released when a CTA starts its last tile (pdl_late), they only cover this kernel's tail.
+  if (!p.pdl_late) pdl_launch_dependents();
   pdl_wait();                // everything above touched no global memory; inputs of this kernel are now complete
 
   auto tile_coords = [&](int id, int &w0, int &h0, int &n0, int &c_out0) {
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
           int w0, h0, n0, c_out0;
           tile_coords(id, w0, h0, n0, c_out0);
+          if (p.pdl_late && id + (int)gridDim.x >= total_tiles) pdl_launch_dependents();   // last tile of this CTA
 #pragma unroll 1
           for (int it = 0; it < iters; ++it) {
             const int tap = it / per_tap, cb0 = (it % per_tap) * p.G;
@@ -335,6 +340,7 @@ struct alignas(64) HaloParams {
   uint32_t a_slice_bytes, a_tx, b_bytes, b_stride;
   uint32_t idesc, idesc2;
   int relu;
+  int pdl_late;          // 1: release the programmatic dependents when this CTA starts its LAST item, not at entry
   int vec32;             // out / residual rows are 32-byte aligned: 256-bit epilogue accesses
   const float *bias;
   __half *out_hi, *out_lo;
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_launch_dependents();   // let the next launch start its prologue
+  if (!p.pdl_late) pdl_launch_dependents();   // see conv_umma_kernel
   pdl_wait();                // everything above touched no global memory; inputs of this kernel are now complete
   if (p.dbg && threadIdx.x == 0) {
     p.dbg[blockIdx.x * 16 + 8] = (unsigned long long)(clock64() - c_entry);   // prologue cycles
@@ -442,6 +448,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         for (HaloItem it = item_begin(); item_valid(it); item_next(it)) {
           int n0, h0, c_out0, rows;
           item_get(it, n0, h0, c_out0, rows);
+          if (p.pdl_late) {   // last item of this CTA?
+            HaloItem nx = it;
+            item_next(nx);
+            if (!item_valid(nx)) pdl_launch_dependents();
+          }
           for (int cg = 0; cg < p.ncg; ++cg) {
             long long t0 = clock64();
             mbar_wait(a_empty0 + 8u * slice, aph ^ 1);
@@ -734,6 +745,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------ host side
+// Grid of a persistent kernel over `items` equal work items.  min(items, SMs) leaves a ragged last round: 896 items on
+// 148 CTAs are 8 CTAs with 7 items and 140 with 6, and the 140 SMs then sit under the early-launched (PDL) CTAs of the
+// next layer of the same lane, which wait for the 8 stragglers.  With CTAs = ceil(items / rounds) (896 -> 128 x 7) every
+// CTA finishes together and the SMs the grid does not use run another lane's kernel for the whole time.
+// SHAPY_CONV_EVENGRID=0 restores min(items, SMs).
+static int pdl_late_enabled() {
+  static const int v = []() { const char *e = getenv("SHAPY_PDL_LATE"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
+static int even_grid(int items, int sms) {
+  static const bool on = []() { const char *e = getenv("SHAPY_CONV_EVENGRID"); return !(e && e[0] == '0'); }();
+  if (items <= sms || !on) return std::min(items, sms);
+  const int rounds = ceil_div(items, sms);
+  return ceil_div(items, rounds);
+}
+
 struct UmmaPlan {
   UmmaParams p;
   HaloParams hp;
@@ -895,6 +923,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   p.idesc = (1u << 4) | ((uint32_t)(best.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.idesc2 = (1u << 4) | ((uint32_t)((2 * best.NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.relu = relu;
+  p.pdl_late = pdl_late_enabled();
   p.vec32 = rows_vec32(out, res);
   p.bias = w.bias;
   p.out_hi = out.hi; p.out_lo = out.lo; p.out_ctot = out.Ctot; p.out_coff = out.coff;
@@ -910,7 +939,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->grid = dim3(std::min(p.row_sched ? N * H : p.n_super * p.n_tiles, sms), 1);
+    pl->grid = dim3(p.row_sched ? std::min(N * H, sms) : even_grid(p.n_super * p.n_tiles, sms), 1);
   }
   cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)Wp, (cuuint32_t)best.Hb, (cuuint32_t)best.TN};
   bool ok = true;
@@ -990,6 +1019,7 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
   }
   p.kpt = ceil_div(w.cin, kch);
   p.relu = relu;
+  p.pdl_late = pdl_late_enabled();
   p.vec32 = rows_vec32(out, res);
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B, N>>3 at 17, M>>4 at 24
   p.idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -1027,7 +1057,7 @@ UmmaPlan *umma_plan_create(const ConvW &w, const ActView &in, const ActView &out
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int total = p.tiles_w * p.tiles_h * p.tiles_n * (w.cout / p.NT);
-    pl->grid = dim3(std::min(total, sms), 1);
+    pl->grid = dim3(even_grid(total, sms), 1);
   }
   bool ok = true;
   // activation maps

@@ -31,9 +31,19 @@ def _to_np(array, dtype=np.float32):
     return np.array(array, dtype=dtype)
 
 
+# The 22 body joints of the public SMPL / SMPL-X kinematic tree, in model order.  Pure data (the reference lists the same
+# names first in human_shape/data/utils/keypoint_names.py, SMPLX_KEYPOINT_NAMES = SMPL_KEYPOINT_NAMES[:-2] + ...); the
+# J14 overwrite (body_models.py:184-197) finds its 14 names among exactly these.
+SMPLX_BODY_JOINT_NAMES = [
+    'pelvis', 'left_hip', 'right_hip', 'spine1', 'left_knee', 'right_knee', 'spine2', 'left_ankle', 'right_ankle',
+    'spine3', 'left_foot', 'right_foot', 'neck', 'left_collar', 'right_collar', 'head', 'left_shoulder',
+    'right_shoulder', 'left_elbow', 'right_elbow', 'left_wrist', 'right_wrist']
+
+
 def _keypoint_names(num):
-    """SMPL-X keypoint names come from human_shape.data.utils (pure data) when the reference package is
-    importable; otherwise positional names are used (they only label the output)."""
+    """SMPL-X keypoint names: the reference's own table (human_shape.data.utils, pure data) when that package is
+    importable; otherwise the 22 public body-joint names followed by positional labels (the remaining names only
+    label the output; the J14 overwrite needs the body joints)."""
     try:  # pragma: no cover - only inside the reference environment
         from human_shape.data.utils import KEYPOINT_NAMES_DICT
         names = list(KEYPOINT_NAMES_DICT['smplx'])
@@ -41,7 +51,8 @@ def _keypoint_names(num):
             return names
     except Exception:
         pass
-    return [f'keypoint_{i:03d}' for i in range(num)]
+    names = list(SMPLX_BODY_JOINT_NAMES)
+    return (names + [f'keypoint_{i:03d}' for i in range(len(names), num)])[:max(num, 0)]
 
 
 class SMPLX(nn.Module):
@@ -130,6 +141,9 @@ class SMPLX(nn.Module):
                     if name in J14_NAMES:
                         source.append(idx)
                         target.append(J14_NAMES.index(name))
+                if len(source) != len(J14_NAMES):
+                    raise ValueError(f'J14 regressor: only {len(source)} of the {len(J14_NAMES)} joint names were found '
+                                     'among the model\'s keypoint names; refusing to skip the overwrite silently')
                 self.use_joint_regressor = True
                 self.register_buffer('source_idxs', torch.from_numpy(np.asarray(source, dtype=np.int64)))
                 self.register_buffer('target_idxs', torch.from_numpy(np.asarray(target, dtype=np.int64)))

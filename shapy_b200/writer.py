@@ -11,6 +11,7 @@ trimesh's exporter uses (float x, y, z; list uchar int vertex_indices), readable
 Pure host I/O: no GPU work and no arithmetic beyond demo.py:85-102.
 """
 import os
+import threading
 import os.path as osp
 from collections import defaultdict
 from concurrent.futures import ThreadPoolExecutor
@@ -66,7 +67,7 @@ def write_ply(path: str, vertices: np.ndarray, faces: np.ndarray) -> None:
     rec = np.empty(len(f), dtype=[('n', 'u1'), ('idx', '<i4', (3,))])
     rec['n'] = 3
     rec['idx'] = f
-    tmp = path + '.tmp'
+    tmp = f'{path}.{os.getpid()}.{threading.get_ident()}.tmp'     # unique: two jobs may target the same file
     with open(tmp, 'wb') as fh:
         fh.write(header)
         fh.write(v.tobytes())
@@ -103,8 +104,11 @@ class ResultWriter:
         self.output_folder, self.save_params, self.save_mesh = output_folder, save_params, save_mesh
         self.pool = ThreadPoolExecutor(max_workers=workers)
         self.pending = []
+        self._last = {}
 
-    def _write_one(self, idx, target, stage_out: Dict, hd_params: Dict, faces):
+    def _write_one(self, idx, target, stage_out: Dict, hd_params: Dict, faces, after=None):
+        if after is not None:
+            after.result()                 # an earlier job writes the same files: keep the reference's order (last one wins)
         fname = target.get_field('fname')
         path = output_dir(self.output_folder, target)
         imgfname = fname.split('.')[0]
@@ -117,7 +121,7 @@ class ResultWriter:
                 out_params[key] = val[idx] if per_image else val          # demo.py:340-345
             for key, val in hd_params.items():
                 out_params[key] = val[idx].item() if np.isscalar(val[idx]) else val[idx]
-            tmp = osp.join(path, f'{imgfname}.tmp.npz')
+            tmp = osp.join(path, f'{imgfname}.{os.getpid()}.{threading.get_ident()}.tmp.npz')
             np.savez_compressed(tmp, **out_params)
             os.replace(tmp, osp.join(path, f'{imgfname}.npz'))
 
@@ -125,20 +129,30 @@ class ResultWriter:
         """Queues the files of one batch.  stage_out: the last stage's entries as HOST arrays (numpy, CPU tensors or
         KeypointTensor); they must stay unchanged until flush()/close() -- hand over copies of reused pinned buffers."""
         # tensors / KeypointTensors are stored per image, everything else (faces, dicts) as it is (demo.py:340-345)
+        targets = list(targets)
         host = {}
         for k, v in stage_out.items():
-            per_image = (torch is not None and torch.is_tensor(v)) or hasattr(v, '_t')
+            # per image: tensors / KeypointTensors (demo.py:340-345) and numpy arrays with one row per target; the mesh
+            # topology (`faces`) and anything else is stored whole
+            per_image = (torch is not None and torch.is_tensor(v)) or hasattr(v, '_t') or (
+                isinstance(v, np.ndarray) and k != 'faces' and v.ndim >= 1 and len(v) == len(targets))
             host[k] = (_np(v), per_image)
         if 'faces' in host:
             faces = host['faces'][0]
+        if self.save_mesh and 'vertices' in host and faces is None:
+            raise ValueError('ResultWriter.submit: save_mesh needs the mesh topology (stage_out[\'faces\'] or faces=)')
         hd = {k: np.asarray(v) for k, v in hd_params.items()}
         for idx, target in enumerate(targets):
-            self.pending.append(self.pool.submit(self._write_one, idx, target, host, hd, faces))
+            key = (output_dir(self.output_folder, target), target.get_field('fname').split('.')[0])
+            job = self.pool.submit(self._write_one, idx, target, host, hd, faces, self._last.get(key))
+            self._last[key] = job          # jobs with the same output files run in submission order
+            self.pending.append(job)
 
     def flush(self):
         for f in self.pending:
             f.result()                     # re-raises a writer's exception
         self.pending = []
+        self._last = {}
 
     def close(self):
         self.flush()

@@ -131,3 +131,20 @@ def test_ops_refuse_cpu_tensors(regressor):
         ops.decode_rot6d(torch.zeros(2, 6))
     with pytest.raises(RuntimeError):
         ops.mesh_to_mesh_forward(torch.zeros(1, 2, 3, 3), torch.zeros(1, 4, 3, 3))
+
+
+def test_j14_names_resolve_without_the_reference_package(tmp_path):
+    """A real SHAPY config passes `j14_regressor_path`; the 14 LSP-style names must resolve to the public SMPL-X body
+    joint indices even when human_shape.data.utils is not importable (the overwrite was silently skipped)."""
+    import numpy as np
+    from shapy_b200 import synth
+    from shapy_b200.human_shape.models.body_models.body_models import SMPLX
+    ds = {k: v for k, v in synth.make_smplx().items() if k not in ('extra_joint_regressor', 'source_idxs', 'target_idxs')}
+    path = str(tmp_path / 'SMPLX_to_J14.npy')
+    np.save(path, np.random.default_rng(0).random((14, synth.NUM_VERTS)).astype(np.float32))
+    m = SMPLX(data_struct=ds, j14_regressor_path=path)
+    assert m.use_joint_regressor
+    assert m.source_idxs.tolist() == [1, 2, 4, 5, 7, 8, 12, 15, 16, 17, 18, 19, 20, 21]
+    names = ['right_ankle', 'right_knee', 'right_hip', 'left_hip', 'left_knee', 'left_ankle', 'right_wrist', 'right_elbow',
+             'right_shoulder', 'left_shoulder', 'left_elbow', 'left_wrist', 'neck', 'head']
+    assert [names[t] for t in m.target_idxs.tolist()] == [m.keypoint_names[s] for s in m.source_idxs.tolist()]

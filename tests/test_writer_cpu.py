@@ -80,3 +80,25 @@ def test_batch_files_like_the_demo(tmp_path):
         assert np.allclose(z['transl'], hd['transl'][i]) and float(z['focal_length_in_px']) == 5000
         v, f = writer.read_ply(os.path.join(d, f'img_{i:02d}.ply'))
         assert np.allclose(v, stage['vertices'][i].numpy() + hd['transl'][i].astype(np.float32), atol=1e-6) and np.array_equal(f, faces)
+
+
+def test_same_output_name_and_numpy_inputs(tmp_path):
+    """Two people in one image share `fname`: the jobs must not corrupt each other's temp files and the later one wins (as
+    in the reference's sequential loop); numpy arrays with one row per target are stored per image; a mesh without
+    topology is refused up front."""
+    rng = np.random.default_rng(3)
+    targets = [Target(fname='same.jpg', orig_bbox_size=200.0, orig_center=np.float32([10, 20])) for _ in range(6)]
+    verts = rng.normal(size=(6, 50, 3)).astype(np.float32)
+    faces = rng.integers(0, 50, (30, 3))
+    hd = dict(transl=np.zeros((6, 3), np.float32), focal_length_in_px=np.full(6, 1000.0), center=np.zeros((6, 2)),
+              focal_length_in_mm=np.full(6, 50.0), sensor_width=np.full(6, 36.0))
+    with writer.ResultWriter(str(tmp_path)) as w:
+        for _ in range(3):
+            w.submit(targets, {'vertices': torch.from_numpy(verts), 'betas': verts[:, 0, :], 'faces': faces}, hd)
+    d = np.load(tmp_path / 'same.npz', allow_pickle=True)
+    assert d['betas'].shape == (3,) and np.allclose(d['vertices'], verts[5])        # last target wins, row 5
+    v, f = writer.read_ply(str(tmp_path / 'same.ply'))
+    assert np.allclose(v, verts[5]) and (f == faces).all()
+    assert not [p for p in os.listdir(tmp_path) if 'tmp' in p]
+    with pytest.raises(ValueError):
+        writer.ResultWriter(str(tmp_path)).submit(targets, {'vertices': torch.from_numpy(verts)}, hd)
