@@ -556,6 +556,8 @@ extern "C" int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t 
         sp[(size_t)(NB * 3 + c) * Vpad + v] = d->v_template[(size_t)v * 3 + c];
       }
     s.shape_planes = upload(m, sp, err);
+    m->h_lbs_weights.assign(d->lbs_weights, d->lbs_weights + (size_t)V * J);
+    m->h_parents = par;
     m->fused_ok = false;
     if (err == cudaSuccess && get_encode()) {
       cuuint64_t dims[4] = {64, (cuuint64_t)Vpad, 3, (cuuint64_t)nKB};
@@ -576,6 +578,7 @@ extern "C" int shapy_smplx_create(shapy_smplx_t **out, const shapy_smplx_desc_t 
 extern "C" void shapy_smplx_destroy(shapy_smplx_t *m) {
   if (!m) return;
   for (void *p : m->allocs) cudaFree(p);
+  for (auto &kv : m->wtiles) if (kv.second.dev) cudaFree(kv.second.dev);
   delete m;
 }
 

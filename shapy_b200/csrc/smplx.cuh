@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace shapy {
@@ -41,6 +44,13 @@ struct shapy_smplx {
   std::vector<void *> allocs;
   CUtensorMap basis_map;                    // (64, Vpad, 3, KPpad / 32) fp16, box (64, 128, 3, 1), SWIZZLE_128B
   bool fused_ok = false;                    // the packed operands above exist and the maps encoded
+  // blend-GEMM operand of the fused kernel: skinning weights folded onto the rotated joints (joints >= n_rot carry
+  // their nearest rotated ancestor's transform), built lazily per n_rot from the host copies below
+  std::vector<float> h_lbs_weights;         // (V, J) dense, as given
+  std::vector<int> h_parents;
+  struct WTiles { __half *dev = nullptr; CUtensorMap map; bool ok = false; };
+  mutable std::mutex wmu;
+  mutable std::map<int, WTiles> wtiles;
 };
 
 namespace shapy {

@@ -38,7 +38,20 @@ constexpr int LG = 32;             // bodies per group = columns of D0 (and of D
 constexpr int LKB = 32;            // k per block: 64-byte rows, SWIZZLE_64B
 constexpr int LStages = 2;
 constexpr int kLbsEpi = 16;        // prologue / epilogue warps (multiple of 4: TMEM lane-quarter rule)
-constexpr int kLbsThreads = 64 + 32 * kLbsEpi;
+constexpr int kLbsCtl = 4;         // control warps: TMA producer, MMA issuer, two idle (a warpgroup of its own, see setmaxnreg)
+constexpr int kLbsThreads = 32 * (kLbsCtl + kLbsEpi);
+// The register file is 16 K registers per SM sub-partition and warps go to sub-partitions round robin: 5 warps per
+// sub-partition cap a uniform allocation at 96 registers, where the epilogue rematerialises addresses all over the place
+// (ncu r02: 13 % of its instructions).  The control warpgroup hands its registers over instead (setmaxnreg acts on
+// whole warpgroups, which is why the two roles that need few registers got a warpgroup to themselves):
+// 32 + 4 x 112 = 480 = the 5 x 96 the sub-partition's warps were launched with (setmaxnreg only moves registers inside
+// the CTA's launch allocation: asking for more than the control warps released blocks forever).
+constexpr int kLbsCtlRegs = 32, kLbsEpiRegs = 112;
+// TMEM columns: two GEMM-1 accumulators at [0, 192) and [256, 448), two blend-GEMM chunk accumulators at [192, 240) and
+// [448, 496).  (Tried: one GEMM-1 accumulator that the epilogue takes into registers up front plus six chunk
+// accumulators, so that chunks are issued far ahead: 857 instead of 777 us at B = 4 096 -- GEMM 1 of the next item then
+// starts later, and it is paced by TMA at ~20 B/cycle/SM with the L2 at two thirds of its throughput cap.)
+constexpr int kTvBufs = 2;
 constexpr int kLbsMaxKB = 6;       // k-blocks of the pose feature that fit next to everything else (n_rot <= 22: SHAPY)
 constexpr int kLbsNB = 10;         // shape coefficients held in registers
 constexpr int kLbsPairs = (LG * kMaxJoints + 32 * kLbsEpi - 1) / (32 * kLbsEpi);   // (body, joint) pairs per prologue thread
@@ -46,15 +59,26 @@ constexpr uint32_t kPlaneBytes = LV * 128;                // 16 KB: one coordina
 constexpr uint32_t kStageBytes = 3 * kPlaneBytes;         // 48 KB: one TMA box
 constexpr uint32_t kCoefBlkBytes = 2 * LG * LKB * 2;      // 4 KB: [C_hi rows | C_lo rows] of one k-block
 constexpr float kLoInvL = 1.0f / 2048.0f;
+// TV variant: the skinning transform blend T_v = sum_j w_vj A_j as a second tcgen05 GEMM
+constexpr int kTvJ = 32;                                   // joint columns (K) of the blend GEMM: rotated joints, padded
+constexpr int kTvChunk = 4;                                // bodies per chunk (one from each epilogue part): N = 48
+constexpr int kTvN = kTvChunk * 12;
+constexpr uint32_t kTvBlkBytes = kTvN * kTvJ * 2;          // 3 072 B: [48 rows][32 joints] fp16, 64-byte rows (SWIZZLE_64B)
+constexpr uint32_t kTvOpBytes = (LG / kTvChunk) * 2 * kTvBlkBytes;   // 8 chunks x (hi, lo) = 49 152 B
+constexpr uint32_t kTvWBytes = LV * 128;                   // W tile: 128 rows x [hi 32 | lo 32] fp16 = 16 KB (SWIZZLE_128B)
+constexpr float kTvWScale = 1024.0f, kTvAScale = 64.0f;    // operands are scaled so that their fp16 residuals stay normal
 
 struct alignas(64) LbsParams {
   CUtensorMap basis;
+  CUtensorMap wmap;           // TV: folded skinning weights (64, Vpad) fp16 [hi 32 | lo 32], box (64, 128), SWIZZLE_128B
   SmplxDev m;
   const float *betas, *rot;
   int n_rot, B, Kp, nkb, n_vt, n_items;
   float *vertices, *v_shaped, *joints;
   int *lut;
-  uint32_t idesc64, idesc32;
+  uint32_t idesc64, idesc32, idesc48;
+  int dbg_flags;    // SHAPY_LBS_DBGFLAGS experiments: 1 = no output stores, 2 = blocking producer waits
+  int dbg_lt;       // first of the two items per CTA whose epilogue is stamped
   long long *dbg;   // optional [gridDim.x][32] cycle stamps (SHAPY_LBS_DEBUG=1)
 };
 
@@ -62,6 +86,34 @@ struct alignas(64) LbsParams {
 // (Swizzle<2,4,3>: address bits [5:4] ^= bits [8:7]); the block base is 1024-byte aligned
 __device__ __forceinline__ uint32_t sw64_off(int r, int kk) {
   return (uint32_t)(r * 64 + ((((kk >> 3) ^ (r >> 1)) & 3) << 4) + (kk & 7) * 2);
+}
+
+// wait of a role with slack (the TMA producer): back off between polls instead of competing for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kLbsEpi) : "memory"); }
@@ -72,6 +124,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
                : "r"(taddr));
 }
 
+template <bool TV>
 __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_constant__ LbsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmplxDev &m = p.m;
@@ -81,8 +134,13 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   const uint32_t stage0 = smem_base;
   const uint32_t coef0 = stage0 + LStages * kStageBytes;
   const uint32_t aj_off = LStages * kStageBytes + kLbsMaxKB * kCoefBlkBytes;
-  float *Aj = reinterpret_cast<float *>(smem_gen + aj_off);                        // [LG][J][12]
-  const uint32_t betas_off = aj_off + (uint32_t)(LG * m.J * 12 * 4);
+  // !TV: A_j fp32 [LG][J][12].  TV: the same region first stages the rotations, then holds A_j fp32 of the rotated
+  // joints [LG][kTvJ][12] during the chain, and finally the B operand of the blend GEMM (written from registers)
+  float *Aj = reinterpret_cast<float *>(smem_gen + aj_off);
+  const int AJ = TV ? kTvJ : m.J;                                                  // joint stride of the fp32 A_j array
+  const uint32_t aj_bytes = TV ? kTvOpBytes : (uint32_t)(LG * m.J * 12 * 4);
+  const uint32_t wt_off = aj_off + aj_bytes;                                       // TV: W tile (1 024-aligned: all sizes above are)
+  const uint32_t betas_off = wt_off + (TV ? 2u * kTvWBytes : 0u);
   float *betas_s = reinterpret_cast<float *>(smem_gen + betas_off);                // [LG][12]
   const uint32_t rowst_off = betas_off + LG * 12 * 4;
   float *rowst = reinterpret_cast<float *>(smem_gen + rowst_off);                  // [kLbsEpi][2][100]
@@ -94,12 +152,19 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   const uint32_t acc_full0 = bar_base + 16u * LStages;   // [2]
   const uint32_t acc_empty0 = acc_full0 + 16u;           // [2]
   const uint32_t coef_full = acc_empty0 + 16u;
-  const uint32_t tmem_slot = coef_full + 8u;
+  const uint32_t acc2_full0 = coef_full + 8u;            // TV: [kTvBufs] blend-GEMM chunk accumulators
+  const uint32_t acc2_empty0 = acc2_full0 + 8u * kTvBufs;   // [kTvBufs]
+  const uint32_t aop_full = acc2_empty0 + 8u * kTvBufs;  // TV: A_j operand of the group is written
+  const uint32_t w_full0 = aop_full + 8u, w_empty0 = w_full0 + 16u;   // TV: [2] skinning-weight tiles
+  const uint32_t tmem_slot = w_empty0 + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // kinematic-tree tables (a few hundred bytes): read from shared memory inside the level loop
-  __shared__ int s_parents[kMaxJoints], s_level_joints[kMaxJoints], s_level_off[kMaxJoints + 1];
-  for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_parents[i] = m.parents[i]; s_level_joints[i] = m.level_joints[i]; }
-  for (int i = threadIdx.x; i <= m.n_levels; i += blockDim.x) s_level_off[i] = m.level_off[i];
+  __shared__ unsigned char s_parents[kMaxJoints], s_level_joints[kMaxJoints], s_level_off[kMaxJoints + 1], s_anc[kMaxJoints];
+  for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_parents[i] = (unsigned char)max(m.parents[i], 0); s_level_joints[i] = (unsigned char)m.level_joints[i]; }
+  if (threadIdx.x == 0) {   // nearest ancestor with its own rotation (joints >= n_rot are identity: A_j == A_anc(j))
+    for (int j = 0; j < m.J; ++j) s_anc[j] = (unsigned char)(j < p.n_rot ? j : s_anc[max(m.parents[j], 0)]);
+  }
+  for (int i = threadIdx.x; i <= m.n_levels; i += blockDim.x) s_level_off[i] = (unsigned char)m.level_off[i];
   for (int i = threadIdx.x; i < m.J * 3 * 12; i += blockDim.x) {
     const int r = i / 12, l = i % 12;
     jtab[i] = l < m.NB ? m.J_dirs[(size_t)r * m.NC + l] : (l == m.NB ? m.J_template[r] : 0.f);
@@ -109,6 +174,9 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
     for (int s = 0; s < LStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full0 + 8u * i, 1); mbar_init(acc_empty0 + 8u * i, kLbsEpi); }
     mbar_init(coef_full, kLbsEpi);
+    for (int i = 0; i < kTvBufs; ++i) { mbar_init(acc2_full0 + 8u * i, 1); mbar_init(acc2_empty0 + 8u * i, kLbsEpi); }
+    mbar_init(aop_full, kLbsEpi);
+    for (int i = 0; i < 2; ++i) { mbar_init(w_full0 + 8u * i, 1); mbar_init(w_empty0 + 8u * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -129,15 +197,24 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   const int it_lo = (int)((long long)p.n_items * blockIdx.x / gridDim.x);
   const int it_hi = (int)((long long)p.n_items * (blockIdx.x + 1) / gridDim.x);
 
+  if (warp < kLbsCtl) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kLbsCtlRegs));
   if (warp == 0) {
     // ===================================================================== TMA producer: pose-basis k-blocks
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int it = it_lo; it < it_hi; ++it) {
+      int lt = 0;
+      for (int it = it_lo; it < it_hi; ++it, ++lt) {
         const int vt = it % p.n_vt;
+        if (TV) {   // skinning-weight tile of this vertex tile (two buffers: freed by the item's last blend MMA)
+          mbar_wait_relaxed(w_empty0 + 8u * (lt & 1), (uint32_t)(((lt >> 1) & 1) ^ 1));
+          mbar_expect_tx(w_full0 + 8u * (lt & 1), kTvWBytes);
+          tma_load_2d(smem_base + wt_off + (uint32_t)(lt & 1) * kTvWBytes, &p.wmap, w_full0 + 8u * (lt & 1), 0, vt * LV);
+        }
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1);
+          if (p.dbg_flags & 2) mbar_wait(empty_bar(s), ph ^ 1);
+          else mbar_wait_relaxed(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), kStageBytes);
           const uint32_t sb = stage0 + s * kStageBytes;
           tma_load_4d(sb, &p.basis, full_bar(s), 0, vt * LV, 0, kb);
@@ -147,62 +224,118 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    int s = 0, lt = 0, gprev = -1, gchanges = 0;
-    uint32_t ph = 0;
-    for (int it = it_lo; it < it_hi; ++it, ++lt) {
-      const int g = it / p.n_vt;
-      if (g != gprev) {   // the epilogue warps rebuild the pose features of the new group
-        mbar_wait(coef_full, (uint32_t)(gchanges & 1));
-        ++gchanges;
-        gprev = g;
-        if (lane == 0 && lt == 0) stamp(16);
-      }
-      const int buf = lt & 1;
-      const uint32_t aph = (lt >> 1) & 1;
-      mbar_wait(acc_empty0 + 8u * buf, aph ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t dhi = desc_hi_swz<LKB>();       // B operand: 64-byte rows, SWIZZLE_64B
-        const uint32_t ahi = desc_hi_swz<64>();        // A operand: 128-byte rows [hi | lo], SWIZZLE_128B
-        const uint32_t dbase = tmem_base + buf * 256u;
-        int s_l = s;
-        uint32_t ph_l = ph;
-#pragma unroll 1
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(full_bar(s_l), ph_l);
-          tc_fence_after();
-          const uint32_t a16 = desc_lo_swz(stage0 + s_l * kStageBytes);
-          const uint32_t b16 = desc_lo_swz(coef0 + kb * kCoefBlkBytes);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint32_t ac = a16 + c * (kPlaneBytes >> 4), d = dbase + c * 64u;
-#pragma unroll
-            for (int ks = 0; ks < LKB / 16; ++ks) {
-              // [D0 | D1] (+)= P_hi . [C_hi | C_lo]^T ; D1 += P_lo . C_hi^T
-              umma_f16_lh(d, ac + 2 * ks, ahi, b16 + 2 * ks, dhi, p.idesc64, (kb | ks) ? 1u : 0u);
-              umma_f16_lh(d + LG, ac + 4 + 2 * ks, ahi, b16 + 2 * ks, dhi, p.idesc32, 1u);   // lo half of the row: +64 B
+    // ===================================================================== MMA issuer (one thread)
+    // Two in-order work queues share the tensor pipe: GEMM 1 (pose blend) k-blocks, which become ready as TMA delivers
+    // them (two in flight: the ring), and -- TV -- the blend-GEMM chunks, which become ready as the epilogue hands the two
+    // chunk accumulators back.  A blocking wait on either would stall the other (measured: the epilogue of item t sat
+    // 6 000 cycles behind the k-block waits of item t + 1), so the thread polls both and issues whatever is ready.
+    if (lane == 0) {
+      const uint32_t dhi = desc_hi_swz<LKB>();       // B operand of GEMM 1: 64-byte rows, SWIZZLE_64B
+      const uint32_t ahi = desc_hi_swz<64>();        // A operands: 128-byte rows [hi | lo], SWIZZLE_128B
+      const uint32_t ohi = desc_hi_swz<kTvJ>();
+      const uint32_t o16 = desc_lo_swz(smem_base + aj_off);
+      int s = 0;                                     // ring position: k-blocks are consumed in issue order
+      uint32_t ph = 0;
+      int g_it = it_lo, g_kb = 0, g_gprev = -1, g_gch = 0;   // GEMM-1 cursor
+      bool g_open = false;                                   // accumulator of item g_it acquired
+      int c_it = it_lo, c_c = 0, c_gprev = -1, c_gch = 0;    // chunk cursor
+      int c_cb = 0;                                          // chunk accumulator (round robin) and its phase
+      uint32_t c_cph = 0;
+      bool c_open = false;                                   // operands of item c_it are there
+      while (g_it < it_hi || (TV && c_it < it_hi)) {
+        bool progressed = false;
+        if (g_it < it_hi) {
+          const int lt = g_it - it_lo, g = g_it / p.n_vt, buf = lt & 1;
+          const uint32_t eph = (uint32_t)(((lt >> 1) & 1) ^ 1);
+          if (!g_open) {
+            bool ok = true;
+            if (g != g_gprev) {   // the epilogue warps rebuild the pose features of a new group after its last epilogue
+              ok = mbar_test(coef_full, (uint32_t)(g_gch & 1));
+              if (ok) { ++g_gch; g_gprev = g; if (lt == 0) stamp(16); }
+            }
+            if (ok && mbar_test(acc_empty0 + 8u * buf, eph)) {
+              g_open = true;
+              tc_fence_after();
+              if ((unsigned)(lt - p.dbg_lt) < 2u) stamp(13 + lt - p.dbg_lt);
             }
           }
-          umma_commit(empty_bar(s_l));
-          if (++s_l == LStages) { s_l = 0; ph_l ^= 1; }
+          if (g_open && mbar_test(full_bar(s), ph)) {
+            tc_fence_after();
+            const uint32_t a16 = desc_lo_swz(stage0 + s * kStageBytes);
+            const uint32_t b16 = desc_lo_swz(coef0 + g_kb * kCoefBlkBytes);
+            const uint32_t dbase = tmem_base + buf * 256u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const uint32_t ac = a16 + c * (kPlaneBytes >> 4), d = dbase + c * 64u;
+#pragma unroll
+              for (int ks = 0; ks < LKB / 16; ++ks) {
+                // [D0 | D1] (+)= P_hi . [C_hi | C_lo]^T ; D1 += P_lo . C_hi^T
+                umma_f16_lh(d, ac + 2 * ks, ahi, b16 + 2 * ks, dhi, p.idesc64, (g_kb | ks) ? 1u : 0u);
+                umma_f16_lh(d + LG, ac + 4 + 2 * ks, ahi, b16 + 2 * ks, dhi, p.idesc32, 1u);   // lo half of the row: +64 B
+              }
+            }
+            umma_commit(empty_bar(s));
+            if (++s == LStages) { s = 0; ph ^= 1; }
+            if (++g_kb == p.nkb) {
+              umma_commit(acc_full0 + 8u * buf);
+              if ((unsigned)(lt - p.dbg_lt) < 2u) stamp(17 + lt - p.dbg_lt);
+              g_kb = 0; g_open = false; ++g_it;
+            }
+            progressed = true;
+          }
         }
-        umma_commit(acc_full0 + 8u * buf);
-        if (lt < 2) stamp(17 + lt);
+        // blend GEMM chunk c of item c_it: T[v][(part, 12)] = W'[v][j] . A_j[body = part * 8 + c][12]
+        if (TV && c_it < g_it) {
+          const int lt = c_it - it_lo, g = c_it / p.n_vt;
+          if (!c_open) {
+            bool ok = true;
+            if (g != c_gprev) {
+              ok = mbar_test(aop_full, (uint32_t)(c_gch & 1));
+              if (ok) { ++c_gch; c_gprev = g; }
+            }
+            if (ok && mbar_test(w_full0 + 8u * (lt & 1), (uint32_t)((lt >> 1) & 1))) { c_open = true; tc_fence_after(); }
+          }
+          if (c_open && mbar_test(acc2_empty0 + 8u * c_cb, c_cph ^ 1)) {
+            tc_fence_after();
+            const uint32_t w16 = desc_lo_swz(smem_base + wt_off + (uint32_t)(lt & 1) * kTvWBytes);
+            const uint32_t d = tmem_base + (c_cb ? 448u : 192u);
+            const uint32_t bh = o16 + (uint32_t)c_c * ((2 * kTvBlkBytes) >> 4), bl = bh + (kTvBlkBytes >> 4);
+#pragma unroll
+            for (int ks = 0; ks < kTvJ / 16; ++ks) {
+              umma_f16_lh(d, w16 + 2 * ks, ahi, bh + 2 * ks, ohi, p.idesc48, ks ? 1u : 0u);       // W_hi . A_hi
+              umma_f16_lh(d, w16 + 2 * ks, ahi, bl + 2 * ks, ohi, p.idesc48, 1u);                 // W_hi . A_lo
+              umma_f16_lh(d, w16 + 4 + 2 * ks, ahi, bh + 2 * ks, ohi, p.idesc48, 1u);             // W_lo . A_hi
+            }
+            umma_commit(acc2_full0 + 8u * c_cb);
+            if (++c_cb == kTvBufs) { c_cb = 0; c_cph ^= 1; }
+            if (lt == p.dbg_lt && c_c == 0) stamp(12);
+            if (++c_c == LG / kTvChunk) {
+              if (lt == p.dbg_lt) stamp(11);
+              umma_commit(w_empty0 + 8u * (lt & 1));
+              c_c = 0; c_open = false; ++c_it;
+            }
+            progressed = true;
+          }
+        }
+        if (!progressed) __nanosleep(20);
       }
-      __syncwarp();
-      for (int kb = 0; kb < p.nkb; ++kb) { if (++s == LStages) { s = 0; ph ^= 1; } }
     }
+    __syncwarp();
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kLbsEpiRegs));
     // ===================================================================== prologue + epilogue warps
-    const int ew = warp - 2, q = warp & 3, part = ew >> 2;       // TMEM lane quarter, body sub-range
-    const int et = threadIdx.x - 64;                              // 0 .. 511
+    const int ew = warp - kLbsCtl, q = warp & 3, part = ew >> 2;  // TMEM lane quarter, body sub-range
+    const int et = threadIdx.x - 32 * kLbsCtl;                    // 0 .. 511
     const int J = m.J;
     float *myst = rowst + (size_t)ew * 200;                       // two 100-float rows (vertices, v_shaped)
     int lt = 0, gprev = -1;
+    int e_cb = 0;                    // TV: chunk accumulator this warp reads next (round robin) and its phase
+    uint32_t e_cph = 0;
     for (int it = it_lo; it < it_hi; ++it, ++lt) {
       const int g = it / p.n_vt, vt = it % p.n_vt;
       const int b0 = g * LG, nb = min(LG, p.B - b0);
+      if (et == 0 && lt == p.dbg_lt + 1) stamp(10);
       if (g != gprev) {
         gprev = g;
         epi_bar();                       // every warp is done with the previous group's A_j / betas
@@ -216,7 +349,16 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
         }
         {
           const float *src = p.rot + (size_t)b0 * rper;
-          for (int i = et; i < nb * rper; i += 32 * kLbsEpi) rs[i] = __ldg(src + i);
+          const int n = nb * rper;
+          if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // 128-bit loads, all in flight before the first store
+            const int n4 = n >> 2;
+#pragma unroll 4
+            for (int i = et; i < n4; i += 32 * kLbsEpi)
+              reinterpret_cast<float4 *>(rs)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+            if (et < (n & 3)) rs[n4 * 4 + et] = __ldg(src + n4 * 4 + et);
+          } else {
+            for (int i = et; i < n; i += 32 * kLbsEpi) rs[i] = __ldg(src + i);
+          }
         }
         epi_bar();
         // ---- pose features (R[1:] - I) as fp16 hi / lo rows of the B operand
@@ -299,34 +441,93 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
             if (slot < off || slot >= end || bl >= nb) continue;
             const int j = s_level_joints[slot];
             const float *R = Rp[k], *Jc = Jp[k];
-            float *Ao = Aj + ((size_t)bl * J + j) * 12;
+            // fp32 A_j element (body, joint, e): !TV [body][joint][12] (the epilogue reads rows of it as float4);
+            // TV [joint][12][body]: consecutive lanes = consecutive bodies are conflict-free (a [body][32][12] array
+            // puts every body of a warp on the same bank: measured 3 200 instead of 900 cycles per level)
+            // and the body index is XOR-ed with the joint so that the transposing read of the operand conversion below
+            // (lanes = joints of one body) is conflict-free too
+            const int es = TV ? LG : 1;
+            auto abase = [&](int jq) { return TV ? jq * 12 * LG + (bl ^ (jq & (LG - 1))) : (bl * AJ + jq) * 12; };
+            if (TV && j >= p.n_rot) {
+              // identity joint: A_j == A of its nearest rotated ancestor (finished in an earlier level); only the posed
+              // joint is needed: G_j.t = A.t + A.R J_j
+              if (vt == 0 && p.joints) {
+                const float *Aa = Aj + abase(s_anc[j]);
+                float *jo = p.joints + ((size_t)(b0 + bl) * m.K + j) * 3;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                  jo[r] = Aa[(r * 4 + 3) * es] + (Aa[(r * 4) * es] * Jc[0] + Aa[(r * 4 + 1) * es] * Jc[1] + Aa[(r * 4 + 2) * es] * Jc[2]);
+              }
+              continue;
+            }
+            float *Ao = Aj + abase(j);
+            float an[12];
             if (lv == 0) {
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
-                Ao[r * 4 + 0] = R[r * 3]; Ao[r * 4 + 1] = R[r * 3 + 1]; Ao[r * 4 + 2] = R[r * 3 + 2];
-                Ao[r * 4 + 3] = Jc[r] - (R[r * 3] * Jc[0] + R[r * 3 + 1] * Jc[1] + R[r * 3 + 2] * Jc[2]);
+                an[r * 4 + 0] = R[r * 3]; an[r * 4 + 1] = R[r * 3 + 1]; an[r * 4 + 2] = R[r * 3 + 2];
+                an[r * 4 + 3] = Jc[r] - (R[r * 3] * Jc[0] + R[r * 3 + 1] * Jc[1] + R[r * 3 + 2] * Jc[2]);
               }
             } else {
-              const float *Ap = Aj + ((size_t)bl * J + s_parents[j]) * 12;
+              const int pj = TV ? s_anc[s_parents[j]] : s_parents[j];
+              const float *Ap = Aj + abase(pj);
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
-                const float g0 = Ap[r * 4], g1 = Ap[r * 4 + 1], g2 = Ap[r * 4 + 2], gt = Ap[r * 4 + 3];
+                const float g0 = Ap[(r * 4) * es], g1 = Ap[(r * 4 + 1) * es], g2 = Ap[(r * 4 + 2) * es], gt = Ap[(r * 4 + 3) * es];
                 const float n0 = g0 * R[0] + g1 * R[3] + g2 * R[6];
                 const float n1 = g0 * R[1] + g1 * R[4] + g2 * R[7];
                 const float n2 = g0 * R[2] + g1 * R[5] + g2 * R[8];
-                Ao[r * 4 + 0] = n0; Ao[r * 4 + 1] = n1; Ao[r * 4 + 2] = n2;
-                Ao[r * 4 + 3] = (g0 * Jc[0] + g1 * Jc[1] + g2 * Jc[2]) + gt - (n0 * Jc[0] + n1 * Jc[1] + n2 * Jc[2]);
+                an[r * 4 + 0] = n0; an[r * 4 + 1] = n1; an[r * 4 + 2] = n2;
+                an[r * 4 + 3] = (g0 * Jc[0] + g1 * Jc[1] + g2 * Jc[2]) + gt - (n0 * Jc[0] + n1 * Jc[1] + n2 * Jc[2]);
               }
             }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) Ao[e * es] = an[e];
             // posed joint = G_j.t = A_j.t + A_j.R J_j: written once per group (by the CTA that owns vertex tile 0)
             if (vt == 0 && p.joints) {
               float *jo = p.joints + ((size_t)(b0 + bl) * m.K + j) * 3;
 #pragma unroll
               for (int r = 0; r < 3; ++r)
-                jo[r] = Ao[r * 4 + 3] + (Ao[r * 4] * Jc[0] + Ao[r * 4 + 1] * Jc[1] + Ao[r * 4 + 2] * Jc[2]);
+                jo[r] = an[r * 4 + 3] + (an[r * 4] * Jc[0] + an[r * 4 + 1] * Jc[1] + an[r * 4 + 2] * Jc[2]);
             }
           }
           epi_bar();
+        }
+        if (TV) {
+          // ---- A_j of the rotated joints -> B operand of the blend GEMM: rows (part, component) of chunk c = body % 8,
+          // columns = joints, fp16 hi / lo (x 64), K-major SWIZZLE_64B.  The operand overwrites the fp32 array, so
+          // every thread first takes its (body, joint) pairs into registers.
+          // Item i = operand row (chunk c, part, component e) x joint pair: 16 lanes write one 64-byte row as half2.
+          constexpr int kItems = (LG * 12 * kTvJ / 2) / (32 * kLbsEpi);   // 12 per thread
+          float av[kItems][2];
+#pragma unroll
+          for (int k = 0; k < kItems; ++k) {
+            const int i = et + k * 32 * kLbsEpi;
+            const int row = i >> 4, jj = (i & 15) * 2;
+            const int c = row / (4 * 12), prt = (row / 12) & 3, e = row % 12;
+            const int bl = prt * (LG / kTvChunk) + c;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const bool on = bl < nb && jj + h < p.n_rot;
+              av[k][h] = on ? Aj[((jj + h) * 12 + e) * LG + (bl ^ (jj + h))] * kTvAScale : 0.f;
+            }
+          }
+          epi_bar();
+#pragma unroll
+          for (int k = 0; k < kItems; ++k) {
+            const int i = et + k * 32 * kLbsEpi;
+            const int row = i >> 4, jj = (i & 15) * 2;
+            const int c = row / (4 * 12), r48 = row % (4 * 12);
+            uint8_t *blk = smem_gen + aj_off + (size_t)c * (2 * kTvBlkBytes);
+            const __half h0 = __float2half_rn(av[k][0]), h1 = __float2half_rn(av[k][1]);
+            const __half l0 = __float2half_rn(av[k][0] - __half2float(h0)), l1 = __float2half_rn(av[k][1] - __half2float(h1));
+            const uint32_t o = sw64_off(r48, jj);
+            *reinterpret_cast<__half2 *>(blk + o) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2 *>(blk + kTvBlkBytes + o) = __halves2half2(l0, l1);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(aop_full);
         }
         if (et == 0 && lt == 0) stamp(3);
       }
@@ -348,28 +549,37 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
       int ej[4];
 #pragma unroll
       for (int sl = 0; sl < 4; ++sl) {
-        const bool on = vok && sl < m.ell_w_n;
+        const bool on = !TV && vok && sl < m.ell_w_n;
         ew[sl] = on ? __ldg(m.ell_w + (size_t)sl * m.V + v) : 0.f;
         ej[sl] = on ? __ldg(m.ell_idx + (size_t)sl * m.V + v) : 0;
       }
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      if (et == 0 && lt < 2) stamp(4 + 3 * lt);
+      if (et == 0 && (unsigned)(lt - p.dbg_lt) < 2u) stamp(4 + 3 * (lt - p.dbg_lt));
       mbar_wait(acc_full0 + 8u * buf, aph);
-      if (et == 0 && lt < 2) stamp(5 + 3 * lt);
+      if (et == 0 && (unsigned)(lt - p.dbg_lt) < 2u) stamp(5 + 3 * (lt - p.dbg_lt));
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16) + part * 8;
       const int rows_here = min(32, m.V - v0w);      // > 0 for every tile (V > (n_vt - 1) * 128 + 96 is NOT assumed)
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        uint32_t d0[3][4], d1[3][4];
+        // pose offsets of four of this warp's bodies
+        float pp[4][3];
+        {
+          uint32_t d0[3][4], d1[3][4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          tmem_ld4(lane_addr + c * 64 + half * 4, d0[c]);
-          tmem_ld4(lane_addr + c * 64 + LG + half * 4, d1[c]);
+          for (int c = 0; c < 3; ++c) {
+            tmem_ld4(lane_addr + c * 64 + half * 4, d0[c]);
+            tmem_ld4(lane_addr + c * 64 + LG + half * 4, d1[c]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              pp[i][c] = (__uint_as_float(d0[c][i]) + __uint_as_float(d1[c][i]) * kLoInvL) * (1.0f / kPoseScale);
         }
-        tmem_ld_wait();
-        if (half == 1) {   // last TMEM read of this item: hand the accumulator buffer back to the MMA warp
+        if (half == 1) {   // last TMEM read of this item: hand the accumulator buffer back to the MMA thread
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty0 + 8u * buf);
@@ -377,7 +587,26 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int bl = part * 8 + half * 4 + i;
-          if (bl >= nb) break;                                   // warp-uniform
+          uint32_t tv[12];
+          if (TV) {
+            // blend-GEMM chunk c = half * 4 + i holds body `bl` of every part: this warp's 12 columns start at part * 12.
+            // The handshake runs for every chunk, also for bodies past the end of the batch.
+            mbar_wait(acc2_full0 + 8u * e_cb, e_cph);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + (e_cb ? 448u : 192u) + ((uint32_t)(q * 32) << 16) + part * 12;
+            uint32_t t0[4], t1[4], t2[4];
+            tmem_ld4(ta, t0); tmem_ld4(ta + 4, t1); tmem_ld4(ta + 8, t2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { tv[e] = t0[e]; tv[4 + e] = t1[e]; tv[8 + e] = t2[e]; }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc2_empty0 + 8u * e_cb);
+            if (++e_cb == kTvBufs) { e_cb = 0; e_cph ^= 1; }
+            if (bl >= nb) continue;                              // warp-uniform
+          } else {
+            if (bl >= nb) break;                                 // warp-uniform
+          }
           const int b = b0 + bl;
           const float4 q0 = *reinterpret_cast<const float4 *>(betas_s + bl * 12);
           const float4 q1 = *reinterpret_cast<const float4 *>(betas_s + bl * 12 + 4);
@@ -391,10 +620,16 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
           float vp[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            vp[c] = vs[c] + (__uint_as_float(d0[c][i]) + __uint_as_float(d1[c][i]) * kLoInvL) * (1.0f / kPoseScale);
+            vp[c] = vs[c] + pp[i][c];
           }
           float o3[3] = {0.f, 0.f, 0.f};
-          if (vok) {
+          if (TV) {
+            constexpr float kInv = 1.0f / (kTvWScale * kTvAScale);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              o3[r] = (__uint_as_float(tv[r * 4]) * vp[0] + __uint_as_float(tv[r * 4 + 1]) * vp[1] +
+                       __uint_as_float(tv[r * 4 + 2]) * vp[2] + __uint_as_float(tv[r * 4 + 3])) * kInv;
+          } else if (vok) {
             for (int sl = 0; sl < m.ell_w_n; ++sl) {
               const float w = sl < 4 ? (sl == 0 ? ew[0] : (sl == 1 ? ew[1] : (sl == 2 ? ew[2] : ew[3]))) : m.ell_w[(size_t)sl * m.V + v];
               if (w == 0.f) continue;
@@ -407,35 +642,35 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
             }
           }
           // ---- transposed row store: the warp's 32 vertices x 3 coordinates are 96 consecutive floats of body b;
-          // they are staged at the row's offset inside its 16-byte grid so that lanes 0..24 issue aligned 128-bit
-          // stores (head / tail floats of a partially covered chunk are stored one by one)
-          const size_t o = ((size_t)b * m.V + v0w) * 3;
-          const int mis = (int)(o & 3), nfl = rows_here * 3;
+          // staged through shared memory and written as three fully coalesced 128-byte warp stores per array (a
+          // version with aligned 128-bit stores needed a scalar path for the row's head / tail, since rows start at
+          // any 4-byte offset: more instructions than it saved)
+          float *gv = p.vertices + ((size_t)b * m.V + v0w) * 3;
+          const int nfl = rows_here * 3;
           __syncwarp();
           if (vok) {
-            myst[mis + 3 * lane] = o3[0]; myst[mis + 3 * lane + 1] = o3[1]; myst[mis + 3 * lane + 2] = o3[2];
-            myst[100 + mis + 3 * lane] = vs[0]; myst[100 + mis + 3 * lane + 1] = vs[1]; myst[100 + mis + 3 * lane + 2] = vs[2];
+            myst[3 * lane] = o3[0]; myst[3 * lane + 1] = o3[1]; myst[3 * lane + 2] = o3[2];
+            myst[100 + 3 * lane] = vs[0]; myst[100 + 3 * lane + 1] = vs[1]; myst[100 + 3 * lane + 2] = vs[2];
           }
           __syncwarp();
-          const int f0 = 4 * lane;                   // stage index of this lane's chunk
-          if (f0 < mis + nfl && f0 + 4 > mis) {
-            float *gv = p.vertices + (o - mis) + f0;
-            float *gs = p.v_shaped ? p.v_shaped + (o - mis) + f0 : nullptr;
-            if (f0 >= mis && f0 + 4 <= mis + nfl) {
-              *reinterpret_cast<float4 *>(gv) = *reinterpret_cast<const float4 *>(myst + f0);
-              if (gs) *reinterpret_cast<float4 *>(gs) = *reinterpret_cast<const float4 *>(myst + 100 + f0);
-            } else {
+          if (p.dbg_flags & 1) continue;
+          if (nfl == 96) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (f0 + e >= mis && f0 + e < mis + nfl) {
-                  gv[e] = myst[f0 + e];
-                  if (gs) gs[e] = myst[100 + f0 + e];
-                }
+            for (int k = 0; k < 3; ++k) gv[k * 32 + lane] = myst[k * 32 + lane];
+            if (p.v_shaped) {
+              float *gs = p.v_shaped + ((size_t)b * m.V + v0w) * 3;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) gs[k * 32 + lane] = myst[100 + k * 32 + lane];
+            }
+          } else {
+            for (int f = lane; f < nfl; f += 32) {
+              gv[f] = myst[f];
+              if (p.v_shaped) p.v_shaped[((size_t)b * m.V + v0w) * 3 + f] = myst[100 + f];
             }
           }
         }
       }
-      if (et == 0 && lt < 2) stamp(6 + 3 * lt);
+      if (et == 0 && (unsigned)(lt - p.dbg_lt) < 2u) stamp(6 + 3 * (lt - p.dbg_lt));
     }
   }
   tc_fence_before();
@@ -446,22 +681,59 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   }
 }
 
-size_t lbs_smem_bytes(int J) {
-  return 1024 + LStages * kStageBytes + kLbsMaxKB * kCoefBlkBytes + (size_t)LG * J * 12 * 4 + LG * 12 * 4 +
-         kLbsEpi * 2 * 100 * 4 + (size_t)J * 3 * 12 * 4 + 16 + 128;   // + 1 KB of static tables (s_parents ...)
+size_t lbs_smem_bytes(int J, bool tv) {
+  const size_t aj = tv ? (size_t)kTvOpBytes + 2 * kTvWBytes : (size_t)LG * J * 12 * 4;
+  return 1024 + LStages * kStageBytes + kLbsMaxKB * kCoefBlkBytes + aj + LG * 12 * 4 + kLbsEpi * 2 * 100 * 4 +
+         (size_t)J * 3 * 12 * 4 + 16 + 256;   // + 0.5 KB of static tables (s_parents ...)
+}
+
+// Skinning weights folded onto the rotated joints and packed for the blend GEMM: [Vpad][hi 32 | lo 32] fp16 (x 1024),
+// one 2-D tensor map with 128-row boxes.  Built once per n_rot.
+static const shapy_smplx::WTiles *get_wtiles(const shapy_smplx *mm, int n_rot) {
+  std::lock_guard<std::mutex> lk(mm->wmu);
+  auto it = mm->wtiles.find(n_rot);
+  if (it != mm->wtiles.end()) return it->second.ok ? &it->second : nullptr;
+  shapy_smplx::WTiles &w = mm->wtiles[n_rot];
+  const SmplxDev &d = mm->d;
+  if (n_rot > kTvJ || mm->h_lbs_weights.empty() || !get_encode()) return nullptr;
+  std::vector<int> anc(d.J);
+  for (int j = 0; j < d.J; ++j) anc[j] = j < n_rot ? j : anc[std::max(mm->h_parents[j], 0)];
+  std::vector<__half> pk((size_t)d.Vpad * 64, __float2half_rn(0.f));
+  std::vector<float> row(kTvJ);
+  for (int v = 0; v < d.V; ++v) {
+    std::fill(row.begin(), row.end(), 0.f);
+    for (int j = 0; j < d.J; ++j) row[anc[j]] += mm->h_lbs_weights[(size_t)v * d.J + j];
+    for (int k = 0; k < kTvJ; ++k) {
+      const float x = row[k] * kTvWScale;
+      const __half h = __float2half_rn(x);
+      pk[(size_t)v * 64 + k] = h;
+      pk[(size_t)v * 64 + 32 + k] = __float2half_rn(x - __half2float(h));
+    }
+  }
+  if (cudaMalloc((void **)&w.dev, pk.size() * sizeof(__half)) != cudaSuccess) { cudaGetLastError(); w.dev = nullptr; return nullptr; }
+  if (cudaMemcpy(w.dev, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  cuuint64_t dims[2] = {64, (cuuint64_t)d.Vpad};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 128};
+  w.ok = encode(&w.map, w.dev, 2, dims, strides, box, 64);
+  return w.ok ? &w : nullptr;
 }
 
 int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot, int n_rot, int B, float *vertices,
                      float *v_shaped, float *joints, int *lut, cudaStream_t st) {
   const SmplxDev &d = mm->d;
   const int Kp = (n_rot - 1) * 9, nkb = std::max(1, ceil_div(Kp, LKB));
-  if (!mm->fused_ok || !vertices || d.NB != kLbsNB || nkb > kLbsMaxKB || lbs_smem_bytes(d.J) > 226 * 1024)
-    return SHAPY_ERR_UNSUPPORTED;
   static const bool off = []() { const char *e = getenv("SHAPY_LBS_FUSED"); return e && e[0] == '0'; }();
-  if (off) return SHAPY_ERR_UNSUPPORTED;
+  static const bool tv_off = []() { const char *e = getenv("SHAPY_LBS_TV"); return e && e[0] == '0'; }();
+  if (off || !mm->fused_ok || !vertices || d.NB != kLbsNB || nkb > kLbsMaxKB) return SHAPY_ERR_UNSUPPORTED;
+  const shapy_smplx::WTiles *wt = tv_off ? nullptr : get_wtiles(mm, n_rot);
+  const bool tv = wt != nullptr;
+  if (lbs_smem_bytes(d.J, tv) > 226 * 1024) return SHAPY_ERR_UNSUPPORTED;
   LbsParams p;
   memset(&p, 0, sizeof(p));
   p.basis = mm->basis_map;
+  { const char *e = getenv("SHAPY_LBS_DBGFLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
+  if (tv) p.wmap = wt->map;
   p.m = d;
   p.betas = betas; p.rot = rot; p.n_rot = n_rot; p.B = B; p.Kp = Kp; p.nkb = nkb;
   p.n_vt = d.Vpad / LV;
@@ -469,8 +741,10 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
   p.vertices = vertices; p.v_shaped = v_shaped; p.joints = joints; p.lut = lut;
   p.idesc64 = (1u << 4) | ((uint32_t)((2 * LG) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.idesc32 = (1u << 4) | ((uint32_t)(LG >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  static std::atomic<unsigned long long> attr_done{0};
-  SHAPY_CUDA_TRY(set_max_dynamic_smem(smplx_lbs_kernel, 226 * 1024, attr_done));   // + 1 KB static <= 227 KB
+  p.idesc48 = (1u << 4) | ((uint32_t)(kTvN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static std::atomic<unsigned long long> attr_done{0}, attr_done_tv{0};
+  if (tv) SHAPY_CUDA_TRY(set_max_dynamic_smem(smplx_lbs_kernel<true>, 226 * 1024, attr_done_tv));   // + 1.3 KB static <= 227 KB
+  else SHAPY_CUDA_TRY(set_max_dynamic_smem(smplx_lbs_kernel<false>, 226 * 1024, attr_done));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -479,7 +753,7 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kLbsThreads);
-  cfg.dynamicSmemBytes = lbs_smem_bytes(d.J);
+  cfg.dynamicSmemBytes = lbs_smem_bytes(d.J, tv);
   cfg.stream = st;
   static const bool dbg = getenv("SHAPY_LBS_DEBUG") != nullptr;
   if (dbg) {   // synchronous: per-CTA cycle stamps of the roles (prologue / MMA / epilogue phases)
@@ -487,14 +761,17 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
     cudaMalloc(&d, (size_t)grid * 32 * 8);
     cudaMemset(d, 0, (size_t)grid * 32 * 8);
     p.dbg = d;
-    SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel, p));
+    p.dbg_lt = p.n_items / grid > 10 ? 8 : 0;
+    if (tv) SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel<true>, p));
+    else SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel<false>, p));
     cudaStreamSynchronize(st);
     std::vector<long long> h((size_t)grid * 32);
     cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     const char *names[32] = {"", "coef_ready", "pairs_loaded", "chain_done", "it0_consts", "it0_acc_full", "it0_epi_done",
-                             "it1_consts", "it1_acc_full", "it1_epi_done", "", "", "", "", "", "", "mma_coef_wait",
-                             "mma_it0_issued", "mma_it1_issued", "", "", "", "", "", "", "", "", "", "", "", "", "exit"};
+                             "it1_consts", "it1_acc_full", "it1_epi_done", "it1_top", "mma_it0_chunks_done", "mma_it0_chunk0", "mma_it0_g1_open", "mma_it1_g1_open",
+                             "", "mma_coef_wait", "mma_it0_issued", "mma_it1_issued", "c0_ready", "c1_ready", "c2_ready",
+                             "c3_ready", "c4_ready", "c5_ready", "c6_ready", "c7_ready", "c6_wait", "c7_wait", "", "", "exit"};
     fprintf(stderr, "[lbs] B %d items %d grid %d: cycles since kernel entry (avg / max over CTAs that reached the point)\n", B, p.n_items, grid);
     for (int k = 0; k < 32; ++k) {
       if (!names[k][0]) continue;
@@ -505,7 +782,8 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
     count_launch();
     return SHAPY_OK;
   }
-  SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel, p));
+  if (tv) SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel<true>, p));
+  else SHAPY_CUDA_TRY(cudaLaunchKernelEx(&cfg, smplx_lbs_kernel<false>, p));
   count_launch();
   return SHAPY_OK;
 }
