@@ -183,6 +183,8 @@ def a2b_forward(features_m: torch.Tensor, gender, males, females, features_f: to
     ws = [t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in (wm, bm, wf, bf)]
     fm, ff = features_m.contiguous().float(), features_f.contiguous().float()
     out = torch.empty(fm.shape[0], wm.shape[0], dtype=torch.float32, device=dev)
+    if fm.shape[0] == 0:
+        return out
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().shapy_a2b_forward(_lib.ptr(fm), _lib.ptr(ff), _lib.ptr(gender), _lib.ptr(ws[0]), _lib.ptr(ws[1]),
                                                 _lib.ptr(ws[2]), _lib.ptr(ws[3]), fm.shape[0], n, wm.shape[0], 0 if poly else 1,
@@ -220,6 +222,8 @@ def b2a_forward(betas: torch.Tensor, gender: torch.Tensor, males, females) -> to
     gender = gender.to(device=dev, dtype=torch.int32).contiguous()
     ws = [t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in (wm, bm, wf, bf)]
     out = torch.empty(betas.shape[0], wm.shape[0], dtype=torch.float32, device=dev)
+    if betas.shape[0] == 0:
+        return out
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().shapy_b2a_forward(_lib.ptr(betas), _lib.ptr(gender), _lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]),
                                                 _lib.ptr(ws[3]), betas.shape[0], n, wm.shape[0], _lib.ptr(out), _lib.stream_ptr()),

@@ -397,7 +397,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (!p.pdl_late) pdl_launch_dependents();   // see conv_umma_kernel
-  pdl_wait();                // everything above touched no global memory; inputs of this kernel are now complete
+  // Everything above touched no global memory.  The wait for the predecessor grid is taken per role: the weights are
+  // constants, so their producer (warp 1) starts at once and the 83 KB of a resident 48-channel layer land while the
+  // predecessor's last CTAs are still running; the activation producer and the epilogue (residual reads, output
+  // writes) wait; the MMA issuers only touch shared memory / TMEM.
+  if (p.pdl_late < 2 || warp == 0 || warp >= kHaloProd + kHaloIssue) pdl_wait();   // pdl_late == 2: per-role wait
   if (p.dbg && threadIdx.x == 0) {
     p.dbg[blockIdx.x * 16 + 8] = (unsigned long long)(clock64() - c_entry);   // prologue cycles
     p.dbg[blockIdx.x * 16 + 9] = g_entry;                                     // ns timestamp at entry
@@ -751,7 +755,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 // CTA finishes together and the SMs the grid does not use run another lane's kernel for the whole time.
 // SHAPY_CONV_EVENGRID=0 restores min(items, SMs).
 static int pdl_late_enabled() {
-  static const int v = []() { const char *e = getenv("SHAPY_PDL_LATE"); return (e && e[0] == '0') ? 0 : 1; }();
+  // SHAPY_PDL_LATE: 0 = release at entry, 1 = release at the last tile, 2 = 1 + per-role wait in the halo kernel (measured neutral: profiles/r02_pdl_rolewait_ab.txt); default 1
+  static const int v = []() { const char *e = getenv("SHAPY_PDL_LATE"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
   return v;
 }
 

@@ -59,6 +59,8 @@ class v2vhdError(nn.Module):
         B = vi.shape[0]
         error = torch.empty(B, P, dtype=torch.float32, device=dev)
         mean = torch.empty(B, dtype=torch.float32, device=dev)
+        if B == 0:
+            return mean, error
         with torch.cuda.device(dev):
             L = _lib.lib()
             nbytes = L.shapy_p2p_workspace_bytes(B, P)
@@ -123,6 +125,9 @@ class PointError:
         B, V = a.shape[:2]
         error = torch.empty(B, V, dtype=torch.float32, device=dev)
         mean = torch.empty(B, dtype=torch.float32, device=dev)
+        if B == 0 or V == 0:
+            self.last_mean = mean.fill_(float('nan')) if B else mean
+            return error
         with torch.cuda.device(dev):
             L = _lib.lib()
             nbytes = L.shapy_p2p_workspace_bytes(B, V)

@@ -115,6 +115,8 @@ def decode_rot6d(raw: torch.Tensor) -> torch.Tensor:
     B = raw.shape[0]
     n = raw.numel() // 6
     out = torch.empty(n, 3, 3, dtype=torch.float32, device=raw.device)
+    if n == 0:            # empty batch: nothing to launch (torch semantics: empty in, empty out)
+        return out.view(B, raw.shape[1] // 6 if raw.dim() > 1 else 0, 3, 3)
     with torch.cuda.device(raw.device):
         check(lib().shapy_decode_rot6d(ptr(raw), n, ptr(out), stream_ptr()), 'decode_rot6d')
     return out.view(B, -1, 3, 3)
@@ -136,6 +138,8 @@ def smplx_forward(model: SmplxModel, betas, rot, expr=None, camera=None, want_ve
     v_shaped = mk(B, model.V, 3) if want_v_shaped else None
     joints = mk(B, model.K, 3) if want_joints else None
     proj = mk(B, model.K, 2) if (want_joints and camera is not None) else None
+    if B == 0:
+        return dict(vertices=vertices, v_shaped=v_shaped, joints=joints, proj_joints=proj)
     with torch.cuda.device(dev):
         nbytes = lib().shapy_smplx_workspace_bytes(model.handle, B)
         ws = _WS.get('smplx', nbytes, dev)
@@ -149,6 +153,8 @@ def smplx_forward_shape(model: SmplxModel, betas) -> torch.Tensor:
     betas = _cuda_f32(betas, 'betas')
     B = betas.shape[0]
     out = torch.empty(B, model.V, 3, dtype=torch.float32, device=betas.device)
+    if B == 0:
+        return out
     with torch.cuda.device(betas.device):
         check(lib().shapy_smplx_forward_shape(model.handle, ptr(betas), B, ptr(out), stream_ptr()), 'forward_shape')
     return out
@@ -190,6 +196,9 @@ def measure(landmarks: _lib.MeasureLandmarks, v_shaped=None, faces_i32=None, tri
     if return_points:
         pts = torch.zeros(B, 3, max_points, 3, dtype=torch.float32, device=dev)
         cnt = torch.zeros(B, 3, dtype=torch.int32, device=dev)
+    if B == 0:
+        out.status = status
+        return (out, pts, cnt, status) if return_points else out
     with torch.cuda.device(dev):
         if triangles is not None:
             check(lib().shapy_measure_forward_tris(ptr(x), B, F, C.byref(landmarks), ptr(out), ptr(pts), ptr(cnt),
@@ -221,6 +230,10 @@ def mesh_to_mesh_forward(query_triangles, target_triangles, max_collisions=16, p
     M = int(max_collisions)
     faces = torch.empty(B, Q * M, dtype=torch.int64, device=dev)
     bcs = torch.empty(B, Q * M, 2, 3, dtype=torch.float32, device=dev)
+    if B == 0 or Q == 0:
+        return [faces, bcs]
+    if F == 0:            # nothing to collide with: every slot is "no collision"
+        return [faces.fill_(-1), bcs.zero_()]
     with torch.cuda.device(dev):
         nbytes = lib().shapy_mmi_workspace_bytes(B, Q, F)
         ws = _WS.get('mmi', nbytes, dev)
@@ -237,6 +250,8 @@ def head_forward(feats, W0, b0, W1, b1, W2, b2, mean, num_stages=3):
     h0, h1 = W0.shape[0], W1.shape[0]
     out = torch.empty(num_stages, B, P, dtype=torch.float32, device=feats.device)
     ts = [_cuda_f32(t, 'head weight') for t in (W0, b0, W1, b1, W2, b2, mean)]
+    if B == 0:
+        return out
     with torch.cuda.device(feats.device):
         nbytes = lib().shapy_head_workspace_bytes(B, Fd, P, h0, h1)
         ws = _WS.get('head', nbytes, feats.device)
@@ -262,6 +277,8 @@ def head_forward_collapsed(feats, MfT, Mp, c, mean, num_stages=3):
     P = mean.numel()
     out = torch.empty(num_stages, B, P, dtype=torch.float32, device=feats.device)
     ts = [_cuda_f32(t, 'head matrix') for t in (MfT, Mp, c, mean)]
+    if B == 0:
+        return out
     with torch.cuda.device(feats.device):
         ws = _WS.get('headc', B * P * 4, feats.device)
         check(lib().shapy_head_forward_collapsed(ptr(feats), B, Fd, P, *[ptr(t) for t in ts], num_stages, ptr(out),
@@ -321,6 +338,10 @@ class HrnetPlan:
         if Cc != 3:
             raise RuntimeError('images must be (B, 3, H, W)')
         feats = torch.empty(B, self.feat_dim, dtype=torch.float32, device=images.device)
+        if H % 32 or W % 32 or H == 0 or W == 0:
+            raise RuntimeError(f'image size {H}x{W} must be a multiple of 32')
+        if B == 0:
+            return feats
         with torch.cuda.device(images.device):
             nbytes = lib().shapy_hrnet_workspace_bytes(self.handle, B, H, W)
             if nbytes == 0:
