@@ -160,9 +160,15 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // kinematic-tree tables (a few hundred bytes): read from shared memory inside the level loop
   __shared__ unsigned char s_parents[kMaxJoints], s_level_joints[kMaxJoints], s_level_off[kMaxJoints + 1], s_anc[kMaxJoints];
+  __shared__ int s_nlv_rot;   // levels that hold a rotated joint (the deeper ones are identity joints only)
   for (int i = threadIdx.x; i < m.J; i += blockDim.x) { s_parents[i] = (unsigned char)max(m.parents[i], 0); s_level_joints[i] = (unsigned char)m.level_joints[i]; }
   if (threadIdx.x == 0) {   // nearest ancestor with its own rotation (joints >= n_rot are identity: A_j == A_anc(j))
     for (int j = 0; j < m.J; ++j) s_anc[j] = (unsigned char)(j < p.n_rot ? j : s_anc[max(m.parents[j], 0)]);
+    int nl = 0;
+    for (int lv = 0; lv < m.n_levels; ++lv)
+      for (int sl = m.level_off[lv]; sl < m.level_off[lv + 1]; ++sl)
+        if (m.level_joints[sl] < p.n_rot) nl = lv + 1;
+    s_nlv_rot = nl;
   }
   for (int i = threadIdx.x; i <= m.n_levels; i += blockDim.x) s_level_off[i] = (unsigned char)m.level_off[i];
   for (int i = threadIdx.x; i < m.J * 3 * 12; i += blockDim.x) {
@@ -324,6 +330,7 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kLbsEpiRegs));
+    if (threadIdx.x == 32 * kLbsCtl) stamp(15);
     // ===================================================================== prologue + epilogue warps
     const int ew = warp - kLbsCtl, q = warp & 3, part = ew >> 2;  // TMEM lane quarter, body sub-range
     const int et = threadIdx.x - 32 * kLbsCtl;                    // 0 .. 511
@@ -432,7 +439,10 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
         }
         epi_bar();                       // every thread has its rotations in registers: the A_j region may be written
         if (et == 0 && lt == 0) stamp(2);
-        for (int lv = 0; lv < m.n_levels; ++lv) {
+        // TV: identity joints share the transform of their nearest rotated ancestor, so the levels below the last
+        // rotated joint (the three finger levels of SHAPY's 22-rotation pose) are not walked at all
+        const int n_lv = TV ? s_nlv_rot : m.n_levels;
+        for (int lv = 0; lv < n_lv; ++lv) {
           const int off = s_level_off[lv], end = s_level_off[lv + 1];
 #pragma unroll
           for (int k = 0; k < kLbsPairs; ++k) {
@@ -448,18 +458,7 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
             // (lanes = joints of one body) is conflict-free too
             const int es = TV ? LG : 1;
             auto abase = [&](int jq) { return TV ? jq * 12 * LG + (bl ^ (jq & (LG - 1))) : (bl * AJ + jq) * 12; };
-            if (TV && j >= p.n_rot) {
-              // identity joint: A_j == A of its nearest rotated ancestor (finished in an earlier level); only the posed
-              // joint is needed: G_j.t = A.t + A.R J_j
-              if (vt == 0 && p.joints) {
-                const float *Aa = Aj + abase(s_anc[j]);
-                float *jo = p.joints + ((size_t)(b0 + bl) * m.K + j) * 3;
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-                  jo[r] = Aa[(r * 4 + 3) * es] + (Aa[(r * 4) * es] * Jc[0] + Aa[(r * 4 + 1) * es] * Jc[1] + Aa[(r * 4 + 2) * es] * Jc[2]);
-              }
-              continue;
-            }
+            if (TV && j >= p.n_rot) continue;   // identity joint: see below
             float *Ao = Aj + abase(j);
             float an[12];
             if (lv == 0) {
@@ -492,6 +491,25 @@ __global__ void __launch_bounds__(kLbsThreads, 1) smplx_lbs_kernel(const __grid_
             }
           }
           epi_bar();
+        }
+        if (TV && vt == 0 && p.joints) {
+          // posed identity joints (the CTA that owns vertex tile 0 writes the group's joints): A_j == A of the nearest
+          // rotated ancestor, so G_j.t = A.t + A.R J_j
+#pragma unroll
+          for (int k = 0; k < kLbsPairs; ++k) {
+            const int id = et + k * 32 * kLbsEpi;
+            const int bl = id % LG, slot = id / LG;
+            if (slot >= J || bl >= nb) continue;
+            const int j = s_level_joints[slot];
+            if (j < p.n_rot) continue;
+            const int ja = s_anc[j];
+            const float *Aa = Aj + ja * 12 * LG + (bl ^ (ja & (LG - 1)));
+            const float *Jc = Jp[k];
+            float *jo = p.joints + ((size_t)(b0 + bl) * m.K + j) * 3;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              jo[r] = Aa[(r * 4 + 3) * LG] + (Aa[(r * 4) * LG] * Jc[0] + Aa[(r * 4 + 1) * LG] * Jc[1] + Aa[(r * 4 + 2) * LG] * Jc[2]);
+          }
         }
         if (TV) {
           // ---- A_j of the rotated joints -> B operand of the blend GEMM: rows (part, component) of chunk c = body % 8,
@@ -770,7 +788,7 @@ int launch_lbs_fused(const shapy_smplx *mm, const float *betas, const float *rot
     cudaFree(d);
     const char *names[32] = {"", "coef_ready", "pairs_loaded", "chain_done", "it0_consts", "it0_acc_full", "it0_epi_done",
                              "it1_consts", "it1_acc_full", "it1_epi_done", "it1_top", "mma_it0_chunks_done", "mma_it0_chunk0", "mma_it0_g1_open", "mma_it1_g1_open",
-                             "", "mma_coef_wait", "mma_it0_issued", "mma_it1_issued", "c0_ready", "c1_ready", "c2_ready",
+                             "regs_granted", "mma_coef_wait", "mma_it0_issued", "mma_it1_issued", "c0_ready", "c1_ready", "c2_ready",
                              "c3_ready", "c4_ready", "c5_ready", "c6_ready", "c7_ready", "c6_wait", "c7_wait", "", "", "exit"};
     fprintf(stderr, "[lbs] B %d items %d grid %d: cycles since kernel entry (avg / max over CTAs that reached the point)\n", B, p.n_items, grid);
     for (int k = 0; k < 32; ++k) {
