@@ -102,6 +102,15 @@ def conv_traffic(batch: int, mode: int):
         return json.load(f).get('conv_dram_bytes_per_step')
 
 
+def lbs_traffic(batch: int):
+    """DRAM bytes of one SMPL-X forward (fused LBS + joints kernels) from the committed ncu capture; B=64 only."""
+    path = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if batch != 64 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get('lbs_B64', {}).get('dram_bytes_per_call')
+
+
 def usable_cores() -> int:
     """Host threads this process may really use: CPU affinity, capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
@@ -415,7 +424,10 @@ def main():
                          'kernel': 'conv_halo_kernel / conv_umma_kernel (HRNet forward: all 331 convs + fuse + pool, 4 lanes)',
                          'ms': hr_ms, 'mma_flops_factor': 3 if args.mode else 1, 'peak_source': pk['source']},
             'roofline_lbs': {'bound': 'hbm', 'achieved': lbs_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
-                             'frac': lbs_gbs / pk['hbm'], 'ms': lbs_ms, 'kernel': 'smplx_lbs_kernel (fused tcgen05) + smplx_joints_kernel, B=%d posed' % B},
+                             'frac': lbs_gbs / pk['hbm'], 'ms': lbs_ms, 'traffic': lbs_traffic(B),
+                             'kernel': 'smplx_lbs_kernel (fused tcgen05) + smplx_joints_kernel, B=%d posed; achieved counts the '
+                                       'algorithmic bytes of SURVEY 8d (all 486 pose-basis rows), traffic is what ncu measured: the '
+                                       'rows of identity joints are never read' % B},
             'roofline_shape': {'bound': 'hbm', 'achieved': shp_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
                                'frac': shp_gbs / pk['hbm'], 'ms': shp_ms, 'kernel': 'smplx_shape_kernel, 4096 bodies (config 4)'},
             'roofline_measure': {'bound': 'hbm', 'achieved': meas_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
