@@ -338,6 +338,8 @@ struct alignas(64) HaloParams {
   int a_baseoff;    // 1: put (start >> 7) & 7 into the descriptor's base-offset field for row-shifted starts
   uint32_t part_bytes;   // offset of the lo part inside an A slice
   uint32_t a_slice_bytes, a_tx, b_bytes, b_stride;
+  int n_slices;          // A slices in flight (2 or 3): the load of a slice takes about as long as its MMAs, so two
+                         // leave the issuers waiting ~300 cycles per slice (r02_phases.txt: wait_a); three when smem allows
   uint32_t idesc, idesc2;
   int relu;
   int pdl_late;          // 1: release the programmatic dependents when this CTA starts its LAST item, not at entry
@@ -363,14 +365,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   constexpr int PARTS = SPLIT ? 2 : 1;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;                                  // 2 slices
-  const uint32_t b_base = a_base + 2u * p.a_slice_bytes;              // ring of bstages x PARTS blocks
+  const uint32_t b_base = a_base + (uint32_t)p.n_slices * p.a_slice_bytes;   // ring of bstages x PARTS blocks
   const uint32_t b_stage_bytes = p.b_stride;                          // padded size of the [B_hi | B_lo] pair
   const uint32_t bar_base = b_base + b_stage_bytes * p.bstages;
   auto b_full = [&](int s) { return bar_base + 8u * s; };
   auto b_empty = [&](int s) { return bar_base + 8u * (p.bstages + s); };
-  const uint32_t a_full0 = bar_base + 16u * p.bstages;   // [2]
-  const uint32_t a_empty0 = a_full0 + 16u;               // [2]
-  const uint32_t acc_full0 = a_empty0 + 16u;             // [2]
+  const uint32_t a_full0 = bar_base + 16u * p.bstages;   // [3]
+  const uint32_t a_empty0 = a_full0 + 24u;               // [3]
+  const uint32_t acc_full0 = a_empty0 + 24u;             // [2]
   const uint32_t acc_empty0 = acc_full0 + 16u;           // [2]
   const uint32_t tmem_slot = acc_empty0 + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -381,10 +383,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.bstages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), p.n_iss); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(a_full0 + 8u * i, 1); mbar_init(a_empty0 + 8u * i, p.n_iss);
-      mbar_init(acc_full0 + 8u * i, p.n_iss); mbar_init(acc_empty0 + 8u * i, kEpiWarps);
-    }
+    for (int i = 0; i < 3; ++i) { mbar_init(a_full0 + 8u * i, 1); mbar_init(a_empty0 + 8u * i, p.n_iss); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full0 + 8u * i, p.n_iss); mbar_init(acc_empty0 + 8u * i, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kHaloProd) {
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
             }
             if (p.dbg) { long long t2 = clock64(); atomicAdd(p.dbg + blockIdx.x * 16 + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.dbg + blockIdx.x * 16 + 1, (unsigned long long)(t2 - t1)); }
-            if (++slice == 2) { slice = 0; aph ^= 1; }
+            if (++slice == p.n_slices) { slice = 0; aph ^= 1; }
           }
         }
       }
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           }
           __syncwarp();
           if (!p.b_resident) { bs += 9; while (bs >= bstages) { bs -= bstages; bph ^= 1; } }
-          if (++slice == 2) { slice = 0; aph ^= 1; }
+          if (++slice == p.n_slices) { slice = 0; aph ^= 1; }
         }
         if (rec) atomicAdd(p.dbg + blockIdx.x * 16 + 4, (unsigned long long)(clock64() - m1));
       }
@@ -918,6 +918,7 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   p.b_stride = (uint32_t)align_up((size_t)p.b_bytes * parts, 1024);
   const size_t b_stage = (size_t)p.b_stride;
   p.b_resident = best.bres;
+  p.n_slices = 2;
   if (p.b_resident) {
     p.bstages = 9 * p.ncg;
   } else {
@@ -925,6 +926,11 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
     p.bstages = (int)std::max<size_t>(2, std::min<size_t>(9, avail / b_stage));
   }
   if (2 * (size_t)p.a_slice_bytes + b_stage * p.bstages > 222 * 1024) return false;
+  {
+    // a third A slice when it fits without shrinking the weight ring (SHAPY_CONV_ASLICES=2 for A/B runs)
+    static const int want = []() { const char *e = getenv("SHAPY_CONV_ASLICES"); return (e && e[0] == '2') ? 2 : 3; }();
+    if (want == 3 && 3 * (size_t)p.a_slice_bytes + b_stage * p.bstages <= 222 * 1024) p.n_slices = 3;
+  }
   p.idesc = (1u << 4) | ((uint32_t)(best.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.idesc2 = (1u << 4) | ((uint32_t)((2 * best.NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.relu = relu;
@@ -935,11 +941,12 @@ static bool halo_configure(UmmaPlan *pl, const ConvW &w, const ActView &in, cons
   p.res_hi = res ? res->hi : nullptr; p.res_lo = res ? res->lo : nullptr;
   p.res_ctot = res ? res->Ctot : 0; p.res_coff = res ? res->coff : 0;
   p.dbg = nullptr;
-  pl->smem = 2 * (size_t)p.a_slice_bytes + b_stage * p.bstages + 16 * p.bstages + 128 + 1024;
+  pl->smem = (size_t)p.n_slices * p.a_slice_bytes + b_stage * p.bstages + 16 * p.bstages + 128 + 1024;
   if (getenv("SHAPY_CONV_DEBUG"))
     fprintf(stderr, "[halo] cin %d cout %d %dx%d N %d kch %d: NT %d TN %d R %d MT %d bands %d items %d part %u slice %u bstages %d acc_bufs %d bres %d smem %zu\n",
             w.cin, w.cout, H, W, N, kch, p.NT, p.TN, p.R, p.MT, p.bands, p.n_super * p.n_tiles, p.part_bytes,
             p.a_slice_bytes, p.bstages, p.acc_bufs, p.b_resident, pl->smem);
+  if (getenv("SHAPY_CONV_DEBUG")) fprintf(stderr, "[halo]   A slices in flight: %d\n", p.n_slices);
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
