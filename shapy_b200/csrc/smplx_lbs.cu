@@ -16,13 +16,23 @@
 //              plane, vertex tile), fetched by ONE TMA box per k-block into 128-byte SWIZZLE_128B rows
 //   B operand  pose features of a group of 32 bodies, written by the CTA itself into the swizzled K-major layout
 //   D          TMEM: lane = vertex (128 per tile), column = body; three planes (x, y, z) of [D0 | D1] per tile
-// so that in the epilogue a thread owns ONE vertex: its template / shape-basis / skinning-weight constants are loaded
-// once (coalesced) and reused for every body of the group, the bodies' A_j live in shared memory, and each warp
-// writes 32 consecutive vertices of a body as aligned 128-bit rows (transposed through shared memory).
+// so that in the epilogue a thread owns ONE vertex: its template / shape-basis constants are loaded once (coalesced) and
+// reused for every body of the group.
+//
+// The skinning sum is linear in A_j, so the per-vertex transform T_v = sum_j w_vj A_j is a second, small GEMM (TV = true,
+// the default): A operand = the skinning weights folded onto the rotated joints, [vertex][hi 32 j | lo 32 j] fp16 x 2^10
+// (one TMA box per vertex tile), B operand = the group's A_j x 64 as fp16 hi / lo rows (body, component) written by the
+// CTA after the chain, D = 12 fp32 columns per (vertex, body), produced in 8 chunks of 4 bodies through two chunk
+// accumulators that the epilogue hands back as it reads them.  The epilogue is then three tcgen05.ld and a 3 x 4
+// matrix-vector product per vertex-body instead of up to 12 LDS.128 + 48 FMA (TV = false keeps that path: A_j of all
+// joints in shared memory, ELL skinning weights).  Each warp writes 32 consecutive vertices of a body as three fully
+// coalesced 128-byte stores per output array (transposed through shared memory).
 //
 // Work item = (group of 32 bodies, tile of 128 vertices); persistent CTAs own contiguous item ranges so that the
-// group prologue (betas, pose features, kinematic chain: ~2 us of SIMT work) is paid once per group and CTA.
-// Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..17 prologue + epilogue.
+// group prologue (betas, pose features, kinematic chain: ~13 us of mostly latency) is paid once per group and CTA.
+// Warp roles (20 warps): warp 0 TMA producer, warp 1 TMEM allocator + one-thread MMA issuer polling both GEMMs' queues,
+// warps 2-3 idle (they complete the control warpgroup so that setmaxnreg can move its registers), warps 4..19 prologue
+// + epilogue with 112 registers each.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
