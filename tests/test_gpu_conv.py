@@ -87,6 +87,28 @@ def test_conv_fp16_mode(shape):
     assert rel(y0, y1) < 2e-3      # output is rounded to fp16 in this mode
 
 
+@pytest.mark.parametrize('scale', [300.0, 1.0 / 300.0])
+@pytest.mark.parametrize('shape', [SHAPES[0], SHAPES[1], SHAPES[9]])
+def test_conv_split_mode_activation_ranges(shape, scale):
+    """The hi / lo split keeps ~22 mantissa bits at any magnitude inside fp16's exponent range: activations in the
+    hundreds to low thousands (realistic post-BN HRNet ranges) and in the 1e-3 range (where `lo` lives among fp16's
+    subnormals and is stored scaled by 2^11) give the same relative error as unit-scale ones.  Values beyond
+    65 504 are outside the split representation and are not part of the contract."""
+    from shapy_b200 import ops
+    cin, cout, k, stride, H, W, B = shape
+    x, w, bn, res = _case(*shape, seed=2)
+    x, res = x * scale, res * scale
+    for b in ('mean', 'bias'):
+        bn[b] = bn[b] * scale
+    ref = _ref(x, w, None, bn, stride, res, True)
+    assert float(ref.abs().max()) < 6.0e4
+    y = ops.conv_test(x, w, bn=bn, stride=stride, res_nhwc=res, relu=True, mode=1, engine=0)
+    assert rel(y, ref) < 2e-5, rel(y, ref)
+    # and elementwise where the reference is not tiny: no element loses more than a few fp32 ulps of the tensor scale
+    big = ref.abs() > 1e-2 * ref.abs().max()
+    assert float(((y - ref).abs()[big] / ref.abs()[big]).max()) < 2e-3
+
+
 def test_unsupported_shape_is_reported():
     from shapy_b200 import ops
     x, w, bn, res = _case(*SHAPES[-1])
