@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kMeasThreads) measure_kernel(MeasureArgs a) {
         if (nx == sx && nz == sz) break;
       }
     }
-    if (lane == 0) a.out[(size_t)b * 5 + 2 + p] = perim;
+    if (lane == 0) a.out[(size_t)b * 5 + 2 + p] = truncated ? __int_as_float(0x7fc00000) : perim;
   }
 }
 
