@@ -7,7 +7,6 @@ head_vertices_ids) so `model.*` checkpoint entries load; the buffers are the sou
 packed device-side model (shapy_smplx_create) is rebuilt lazily after load_state_dict / .to() / deepcopy.
 The forward pass is three launches of csrc/smplx.cu; there is no PyTorch fallback.
 """
-import os
 import os.path as osp
 import pickle
 from collections import defaultdict

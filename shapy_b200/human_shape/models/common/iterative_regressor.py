@@ -13,7 +13,6 @@ from collections import defaultdict
 import torch
 import torch.nn as nn
 
-from .... import ops as _ops
 from ....attributes import A2B, B2A, a2b_forward, b2a_forward, gender_codes
 from ....body_measurements import BodyMeasurements
 from ..backbone.build import build_backbone

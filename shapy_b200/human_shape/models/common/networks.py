@@ -4,7 +4,6 @@ IterativeRegression 403-592, build_regressor 727-762).  Same module / parameter 
 The nn.Linear objects are parameter containers; the forward runs shapy_head_forward (csrc/head.cu).
 SHAPY_A's head has no activation and no normalisation (configs/b2a_expose_hrnet_demo.yaml:200-207);
 other variants are rejected instead of silently computed differently."""
-import math
 
 import torch
 import torch.nn as nn
